@@ -1,0 +1,230 @@
+"""Generate golden vectors by RUNNING THE UNMODIFIED REFERENCE on CPU (this container only).
+
+    python tests/golden/make_golden.py        # writes tests/golden/*.npz
+
+The reference has no tests or fixtures of its own, so these files are what pins the
+oracle (`oracle/dp_oracle.py`) and, through it, the CUDA engine.  Nothing here is imported by the
+product.  The GPU box has no /root/reference: tests only read the committed .npz files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from _ref_import import import_reference  # noqa: E402
+
+dl = import_reference()
+from deeplens.basics import Ray  # noqa: E402
+from deeplens.monte_carlo import forward_integral, assign_points_to_pixels_small_r, assign_points_to_pixels_big_r  # noqa: E402
+from deeplens.render_psf import local_psf_render_fast  # noqa: E402
+
+torch.set_num_threads(1)          # bit-reproducible reductions / index_put_ order
+LENSES = {"rf50mm": "/root/reference/lenses/rf50mm/lens_web.json",
+          "rf35mm": "/root/reference/lenses/rf35mm/lens_web.json"}
+DP = (0.78, 1.44, 0.3, 0.5)
+
+
+def make_lens(name, res=(512, 768)):
+    return dl.PSFNet(LENSES[name], sensor_res=res, kernel_size=21, device="cpu")
+
+
+def newton_counts(lens, ray):
+    """Trace a copy surface by surface, recording state and the global Newton loop count."""
+    states, counts = [], []
+    for s in lens.surfaces:
+        n_calls = {"n": 0}
+        orig = s.g
+
+        def counting_g(x, y, valid=None, _o=orig, _c=n_calls):
+            _c["n"] += 1
+            return _o(x, y, valid)
+        s.g = counting_g
+        ray = s.ray_reaction(ray)
+        del s.g
+        counts.append(max(n_calls["n"] - 1, 0))       # loop evaluations (one extra strict evaluation)
+        states.append(np.concatenate([ray.o.numpy(), ray.d.numpy(), ray.ra.numpy()[..., None]], -1))
+    return ray, np.stack(states), np.asarray(counts)
+
+
+def golden_setup():
+    out = {}
+    for name in LENSES:
+        lens = make_lens(name)
+        pz, pr = lens.entrance_pupil()
+        epz, epr = lens.exit_pupil()
+        out[f"{name}_scalars"] = np.asarray([lens.aper_idx, lens.hfov, lens.foclen, lens.fnum, pz, pr, epz, epr,
+                                             lens.pixel_size, lens.d_sensor, lens.r_last], np.float64)
+        etas = [[s.mat1.ior(w) / s.mat2.ior(w) for s in lens.surfaces] for w in (0.656, 0.589, 0.486)]
+        out[f"{name}_eta"] = np.asarray(etas, np.float64)
+        torch.manual_seed(0)
+        lens.refocus(-1000 + lens.d_sensor)
+        out[f"{name}_refocus"] = np.asarray([lens.d_sensor, lens.hfov], np.float64)
+        torch.manual_seed(0)
+        out[f"{name}_refocus_u"] = np.stack([torch.rand(2048).numpy(), torch.rand(2048).numpy()])
+    np.savez_compressed(os.path.join(HERE, "setup.npz"), **out)
+
+
+def golden_trace():
+    """Per-surface (o, d, ra) for [spp=256, N=6] bundles, both lenses, three wavelengths for rf50mm."""
+    out = {}
+    for name in LENSES:
+        lens = make_lens(name)
+        ds = lens.d_sensor
+        pts = torch.tensor([[0, 0, -2000 + ds], [0.4, 0.3, -500 + ds], [-0.7, 0.7, -1000.1 + ds],
+                            [0.98, -0.98, -20000 + ds], [0.0, 0.95, -300 + ds], [-0.98, 0.0, -5000 + ds]],
+                           dtype=torch.float32)
+        depth = pts[:, 2]
+        scale = lens.calc_scale_pinhole(depth)
+        obj = pts.clone()
+        obj[:, 0] = pts[:, 0] * scale * lens.sensor_size[1] / 2
+        obj[:, 1] = pts[:, 1] * scale * lens.sensor_size[0] / 2
+        out[f"{name}_points_norm"] = pts.numpy()
+        out[f"{name}_points_obj"] = obj.numpy()
+        out[f"{name}_hfov"] = np.float64(lens.hfov)
+        for wv in ((0.589, 0.656, 0.486) if name == "rf50mm" else (0.589,)):
+            torch.manual_seed(7)
+            u = torch.rand(2, 256)
+            torch.manual_seed(7)
+            ray = lens.sample_from_points(o=obj, spp=256, wvln=wv)
+            pz, pr = lens.entrance_pupil()
+            tag = f"{name}_w{int(wv * 1000)}"
+            out[f"{tag}_u"] = u.numpy()
+            out[f"{tag}_pupil"] = np.asarray([pz, pr], np.float64)
+            out[f"{tag}_ray0"] = np.concatenate([ray.o.numpy(), ray.d.numpy()], -1)
+            ray, states, counts = newton_counts(lens, ray)
+            out[f"{tag}_states"] = states
+            out[f"{tag}_newton"] = counts
+            ray = ray.propagate_to(lens.d_sensor)
+            out[f"{tag}_sensor"] = np.concatenate([ray.o.numpy(), ray.d.numpy(), ray.ra.numpy()[..., None]], -1)
+    # backward + sub-range trace (the entrance-pupil setup trace, optics.py:1335-1376)
+    lens = make_lens("rf50mm")
+    ap = lens.surfaces[lens.aper_idx]
+    phi = torch.linspace(-0.1, 0.1, 16) / 180.0 * torch.pi
+    o = torch.tensor([[1e-3, 0, ap.d.item()]]).repeat(16, 1)
+    d = torch.stack((torch.sin(phi), torch.zeros_like(phi), -torch.cos(phi)), -1)
+    ray = Ray(o, d, device="cpu")
+    out["back_ray0"] = np.concatenate([ray.o.numpy(), ray.d.numpy()], -1)
+    ray, _, _ = lens.trace(ray, lens_range=range(0, lens.aper_idx))
+    out["back_final"] = np.concatenate([ray.o.numpy(), ray.d.numpy(), ray.ra.numpy()[..., None]], -1)
+    np.savez_compressed(os.path.join(HERE, "trace.npz"), **out)
+
+
+def golden_dp():
+    x_tan = torch.linspace(-0.6, 0.6, 241)
+    pts = torch.zeros(241, 2)
+    ra = torch.ones(241)
+    out = {"x_tan": x_tan.numpy()}
+    ks, ps = 21, 0.046875
+    rng = [(-ks / 2 + 0.5) * ps, (ks / 2 - 0.5) * ps]
+    for tag, prm, fn in (("small", DP + ("l",), assign_points_to_pixels_small_r),
+                         ("small_b", (0.6, 1.2, 0.25, 0.45, "l"), assign_points_to_pixels_small_r),
+                         ("big", (0.78, 1.44, 0.3, 0.6, "l"), assign_points_to_pixels_big_r)):
+        dl_, dr_ = [], []
+        for i in range(241):
+            L, R = fn(points=pts[i:i + 1], ks=ks, x_range=rng, y_range=rng, ra=ra[i:i + 1], x_tan=x_tan[i:i + 1],
+                      param_list=prm)
+            dl_.append(L.sum().item())
+            dr_.append(R.sum().item())
+        out[f"{tag}_params"] = np.asarray(prm[:4])
+        out[f"{tag}_dl"] = np.asarray(dl_, np.float32)
+        out[f"{tag}_dr"] = np.asarray(dr_, np.float32)
+    # splat KAT
+    p = torch.tensor([[0.3 * ps, -1.7 * ps]])
+    L, R = assign_points_to_pixels_small_r(points=p, ks=ks, x_range=rng, y_range=rng, ra=torch.ones(1),
+                                           x_tan=torch.tensor([0.0932]), param_list=DP + ("l",))
+    out["kat_L"], out["kat_R"] = L.numpy(), R.numpy()
+    np.savez_compressed(os.path.join(HERE, "dp_weights.npz"), **out)
+
+
+def golden_psf():
+    """psf_diff L/R on identical samples + centres; ks=21 and ks=11; small_r, big_r; RGB."""
+    out = {}
+    for name, spp in (("rf50mm", 200000), ("rf35mm", 200000)):
+        lens = make_lens(name)
+        ds = lens.d_sensor
+        pts = torch.tensor([[0, 0, -2000 + ds], [0.4, 0.3, -700 + ds], [-0.7, 0.7, -1000.1 + ds],
+                            [0.98, -0.98, -20000 + ds], [0.0, 0.9, -300 + ds]], dtype=torch.float32)
+        out[f"{name}_points_norm"] = pts.numpy()
+        out[f"{name}_hfov"] = np.float64(lens.hfov)
+        pz, pr = lens.entrance_pupil()
+        out[f"{name}_pupil"] = np.asarray([pz, pr], np.float64)
+        for tag, prm, ks in (("l", DP + ("l",), 21), ("r", DP + ("r",), 21), ("big_l", (0.78, 1.44, 0.3, 0.6, "l"), 21),
+                             ("big_r", (0.78, 1.44, 0.3, 0.6, "r"), 21), ("ks11_l", DP + ("l",), 11), ("none", None, 21)):
+            torch.manual_seed(3)
+            u = [torch.rand(spp).numpy() for _ in range(2)] + [torch.rand(2048).numpy() for _ in range(2)]
+            torch.manual_seed(3)
+            psf = lens.psf_diff(pts, ks=ks, spp=spp, param_list=prm)
+            out[f"{name}_{tag}"] = psf.numpy()
+            # samples are NOT stored: torch's CPU generator is portable, tests redraw them from the seed;
+            # these checksums guard that assumption
+            out[f"{name}_u_check"] = np.asarray([float(v.astype(np.float64).sum()) for v in u] + [spp])
+        # the chief-ray centre alone, same RNG position (after the main bundle draws)
+        torch.manual_seed(3)
+        torch.rand(spp), torch.rand(spp)
+        depth = pts[:, 2]
+        scale = lens.calc_scale_pinhole(depth)
+        obj = pts.clone()
+        obj[:, 0] = pts[:, 0] * scale * lens.sensor_size[1] / 2
+        obj[:, 1] = pts[:, 1] * scale * lens.sensor_size[0] / 2
+        out[f"{name}_centre"] = lens.psf_center(obj).numpy()
+        out[f"{name}_points_obj"] = obj.numpy()
+        # unnormalised L from forward_integral with pointc_ref=None (RMS centre)
+        torch.manual_seed(3)
+        ray = lens.sample_from_points(o=obj, spp=spp)
+        ray = lens.trace2sensor(ray)
+        out[f"{name}_rms_raw"] = forward_integral(ray, ps=lens.pixel_size, ks=21, pointc_ref=None).numpy()
+        out[f"{name}_chief_raw"] = forward_integral(ray, ps=lens.pixel_size, ks=21,
+                                                    pointc_ref=torch.from_numpy(out[f"{name}_centre"])).numpy()
+        if name == "rf50mm":
+            torch.manual_seed(3)
+            out["rf50mm_rgb"] = lens.psf_rgb(pts[:2], ks=21, spp=4000).numpy()
+    np.savez_compressed(os.path.join(HERE, "psf.npz"), **out)
+
+
+def golden_render():
+    torch.manual_seed(11)
+    lens = make_lens("rf50mm", res=(32, 48))
+    out = {}
+    for ks, (b, h, w) in ((7, (2, 20, 28)), (21, (1, 16, 24))):
+        img = torch.rand(b, 3, h, w)
+        psf = torch.rand(b, h, w, 2, ks, ks) ** 4
+        psf = psf / psf.sum((-1, -2), keepdim=True)
+        rl, rr = local_psf_render_fast(img, psf, ks)
+        out[f"ks{ks}_img"], out[f"ks{ks}_psf"] = img.numpy(), psf.numpy().astype(np.float16)
+        out[f"ks{ks}_psf32_scale"] = np.float32(1.0)
+        out[f"ks{ks}_rl"], out[f"ks{ks}_rr"] = rl.numpy(), rr.numpy()
+        # psf stored as fp16 (the reference casts to half first, so this loses nothing)
+    x = torch.linspace(0, 1, 1001)
+    out["tone_x"] = x.numpy()
+    out["tone_degamma"] = lens.degamma(x.clone()).numpy()
+    out["tone_gamma"] = lens.gamma(lens.degamma(x.clone())).numpy()
+    lum = torch.linspace(0, 1100, 1001)
+    out["tone_lum"] = lum.numpy()
+    out["tone_gamma_lum"] = lens.gamma(lum.clone()).numpy()
+    # full render(): seeded random-init MLP (the real checkpoint is not in the tree)
+    torch.manual_seed(5)
+    lens = dl.PSFNet(LENSES["rf50mm"], sensor_res=(16, 24), kernel_size=21, device="cpu")
+    img = torch.rand(2, 3, 16, 24)
+    depth = -(torch.rand(2, 1, 16, 24) * 9750 + 250)
+    foc = torch.tensor([-1000.0, -1000.0])
+    out["render_img"], out["render_depth"], out["render_foc"] = img.numpy(), depth.numpy(), foc.numpy()
+    out["render_out"] = lens.render(img, depth, foc).numpy()
+    x, y = torch.meshgrid(torch.linspace(-1, 1, 24), torch.linspace(1, -1, 16), indexing="xy")
+    z = lens.depth2z(depth + lens.d_sensor).squeeze(1)
+    o = torch.stack((x[None].repeat(2, 1, 1), y[None].repeat(2, 1, 1), z), -1).float()
+    psf = lens.pred(o.clone()).detach()
+    out["render_psf_probe"] = psf[:, ::5, ::7].numpy()          # a few per-pixel PSFs, fp32
+    # the MLP is re-created from the seed by the tests (torch CPU RNG is portable); pin it by checksums
+    sd = lens.psfnet.state_dict()
+    out["mlp_checksum"] = np.asarray([[v.double().sum().item(), v.double().abs().sum().item()] for v in sd.values()])
+    np.savez_compressed(os.path.join(HERE, "render.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["setup", "trace", "dp", "psf", "render"]
+    for w in which:
+        globals()[f"golden_{w}"]()
+        print("wrote", w)
