@@ -1,0 +1,159 @@
+/*
+ * sdirt_engine.h — C ABI of the B200-native dual-pixel ray-tracing engine (libsdirt_engine.so).
+ *
+ * The reference (LinYark/Sdirt) has no FFI seam: its hot path is eager PyTorch behind Python methods.
+ * Each entry point below replaces the body of one such method; the host-side mirror of the reference
+ * API (sdirt_b200/deeplens/*.py) binds them with ctypes (see INTEGRATION.md for the stub a reference
+ * maintainer would add).  Citations are paths relative to the reference repository.
+ *
+ *   sdirt_lens_create / _set_*      <- Lensgroup.read_lens_json            deeplens/optics.py:2173-2198
+ *                                      Material.ior (Cauchy "n/V")         deeplens/basics.py:316-340
+ *   sdirt_trace_rays                <- Lensgroup.trace/_forward_tracing    deeplens/optics.py:601-717
+ *                                      Aspheric.ray_reaction               deeplens/surfaces.py:391-520
+ *                                      Aspheric._newtons_method/_refract   deeplens/surfaces.py:523-679
+ *                                      Ray.propagate_to                    deeplens/basics.py:256-264
+ *   sdirt_psf_centre                <- Lensgroup.psf_center('chief_ray')   deeplens/optics.py:889-904
+ *   sdirt_psf_bank                  <- Lensgroup.psf_diff                  deeplens/optics.py:934-996
+ *                                      sample_from_points                  deeplens/optics.py:476-494
+ *                                      forward_integral                    deeplens/monte_carlo.py:9-68
+ *                                      assign_points_to_pixels_small_r/big_r  deeplens/monte_carlo.py:135-372
+ *   sdirt_splat_rays                <- forward_integral on an existing Ray deeplens/monte_carlo.py:9-68
+ *   sdirt_render_local_psf          <- local_psf_render_fast               deeplens/render_psf.py:120-155
+ *                                      PSFNet.degamma / gamma / clip       deeplens/psfnet.py:589-620,706-713
+ *
+ * Conventions: every pointer marked "dev" is device memory owned by the caller (a torch CUDA tensor's
+ * data_ptr); the library allocates nothing on the device.  All work is enqueued on `stream`
+ * (a cudaStream_t passed as void*, NULL = legacy default stream) and returns without synchronising.
+ * Return value: 0 on success, negative SDIRT_E_* otherwise; sdirt_last_error() gives the message of the
+ * calling thread's last failure.  Units are millimetres, wavelengths micrometres; float32 arithmetic in
+ * the reference's operation order (IEEE add/mul/div/sqrt, no FMA contraction) unless a flag says otherwise.
+ */
+#ifndef SDIRT_ENGINE_H
+#define SDIRT_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDIRT_MAX_SURFACES 32
+#define SDIRT_MAX_AI 8
+#define SDIRT_MAX_KS 63
+
+enum {
+    SDIRT_OK = 0,
+    SDIRT_E_ARG = -1,      /* bad argument (message says which) */
+    SDIRT_E_CUDA = -2,     /* CUDA runtime error */
+    SDIRT_E_NODEVICE = -3  /* no CUDA device: there is NO CPU fallback */
+};
+
+/* Surface kinds follow the three branches of Aspheric.ray_reaction (surfaces.py:409, 456, 491). */
+enum { SDIRT_SURF_FLAT = 0, SDIRT_SURF_SPHERE = 1, SDIRT_SURF_ASPHERE = 2 };
+
+/* One sequential surface as read from the lens JSON (optics.py:2173-2198). */
+typedef struct sdirt_surface {
+    int32_t kind;                 /* SDIRT_SURF_*; FLAT covers the aperture stop */
+    int32_t n_ai;                 /* number of even-asphere coefficients a2,a4,... (0..8) */
+    int32_t square;               /* flat only: square aperture of half-side r (surfaces.py:416-419) */
+    int32_t reserved;
+    double r;                     /* semi-diameter (python float in the reference) */
+    float d;                      /* vertex z (float32 tensor in the reference) */
+    float c;                      /* curvature */
+    float k;                      /* conic constant */
+    float ai[SDIRT_MAX_AI];
+    double n1_A, n1_B;            /* Cauchy n = A + B/lambda_nm^2 of the object-side medium (basics.py:336-338) */
+    double n2_A, n2_B;            /* image-side medium */
+} sdirt_surface;
+
+typedef struct sdirt_lens sdirt_lens;   /* opaque */
+
+/* Newton iteration control (surfaces.py:543-561).
+ *   per_ray = 1: each ray leaves the loose loop as soon as ITS residual is <= 50e-6 mm (fast path).
+ *   per_ray = 0: replay fixed loop counts, iters[i] loop evaluations at surface i of the lens (this
+ *                reproduces the reference's bundle-global `while any()` count when the caller knows it).
+ * Both are followed by the reference's one extra strict evaluation. */
+typedef struct sdirt_newton {
+    int32_t per_ray;
+    int32_t iters[SDIRT_MAX_SURFACES];
+} sdirt_newton;
+
+/* Dual-pixel sub-aperture model (monte_carlo.py:157-164), pixel units. */
+typedef struct sdirt_dp_params {
+    float h, f, w, r;
+} sdirt_dp_params;
+
+const char *sdirt_last_error(void);
+const char *sdirt_version(void);
+/* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+uint64_t sdirt_launch_count(void);
+/* Device properties the host needs for sizing: SM count of the current device, or <0. */
+int sdirt_device_sm_count(void);
+
+/* ---- lens handle -------------------------------------------------------------------------------- */
+int sdirt_lens_create(const sdirt_surface *surfaces, int n_surfaces, double d_sensor, sdirt_lens **out);
+int sdirt_lens_set_sensor(sdirt_lens *lens, double d_sensor);          /* refocus(), psfnet.py:42-48 */
+int sdirt_lens_set_surface(sdirt_lens *lens, int index, const sdirt_surface *s);  /* set_aperture() etc. */
+int sdirt_lens_num_surfaces(const sdirt_lens *lens);
+/* eta = n_in/n_out at `wvln_um` for each surface, float64 as Material.ior computes it. */
+int sdirt_lens_eta(const sdirt_lens *lens, double wvln_um, int backward, double *eta_out);
+void sdirt_lens_destroy(sdirt_lens *lens);
+
+/* ---- generic trace (Lensgroup.trace / Aspheric.ray_reaction) -------------------------------------
+ * In-place on AoS rays: o[n,3], d[n,3] (unit), ra[n] (0/1 float).  Surfaces [s_begin, s_end) are visited
+ * in ascending order, or descending when backward != 0 (optics.py:666-717).  to_sensor != 0 adds
+ * Ray.propagate_to(d_sensor).  record (optional, dev) receives [s_end-s_begin, n, 7] = (o, d, ra) after
+ * every visited surface. */
+int sdirt_trace_rays(const sdirt_lens *lens, double wvln_um,
+                     float *o_dev, float *d_dev, float *ra_dev, int64_t n,
+                     int s_begin, int s_end, int backward, int to_sensor,
+                     const sdirt_newton *newton, float *record_dev, void *stream);
+
+/* ---- chief-ray PSF centre (Lensgroup.psf_center) --------------------------------------------------
+ * points[N,3] object-space mm; pupil_xy[m,2] samples on the (shrunken) entrance pupil at z = pupil_z,
+ * shared by all points.  centre_out[N,2] = -(ra-weighted centroid of sensor hits). */
+int sdirt_psf_centre(const sdirt_lens *lens, double wvln_um,
+                     const float *points_dev, int64_t n_points,
+                     const float *pupil_xy_dev, int64_t n_samples, double pupil_z,
+                     const sdirt_newton *newton, float *centre_out_dev, void *stream);
+
+/* ---- fused sample -> trace -> DP weights -> splat -> normalise (Lensgroup.psf_diff) ---------------
+ * For every point i and pupil sample j a ray from points[i] towards (pupil_xy[j], pupil_z) is traced to
+ * the sensor, recentred on centre[i], cropped to the ks x ks window of pixel size `pixel_size`, weighted
+ * by the left / right sub-pixel areas and bilinearly splatted into out_l[i], out_r[i] (each [ks,ks]).
+ *   normalise: 0 = raw sums, 1 = divide by (max + 1e-6) as psf_diff does, 2 = divide by the sum.
+ *   workspace_dev: at least sdirt_psf_bank_workspace(...) bytes, contents undefined on entry and exit.
+ *   valid_count_dev (optional): [N] int64, number of rays of each point that reached the window. */
+int64_t sdirt_psf_bank_workspace(int64_t n_points, int64_t n_samples, int ks);
+int sdirt_psf_bank(const sdirt_lens *lens, double wvln_um,
+                   const float *points_dev, int64_t n_points,
+                   const float *pupil_xy_dev, int64_t n_samples, double pupil_z,
+                   const float *centre_dev, int ks, double pixel_size,
+                   const sdirt_dp_params *dp, const sdirt_newton *newton, int normalise,
+                   float *out_l_dev, float *out_r_dev, int64_t *valid_count_dev,
+                   void *workspace_dev, int64_t workspace_bytes, void *stream);
+
+/* ---- splat of already-traced rays (forward_integral) ----------------------------------------------
+ * o[spp,N,3], d[spp,N,3], ra[spp,N] as the reference's Ray holds them (sample-major).  centre_dev may
+ * be NULL: the ra-weighted centroid of each point's hits is used (monte_carlo.py:28-31).  Raw sums. */
+int sdirt_splat_rays(const float *o_dev, const float *d_dev, const float *ra_dev,
+                     int64_t n_samples, int64_t n_points, const float *centre_dev,
+                     int ks, double pixel_size, const sdirt_dp_params *dp,
+                     float *out_l_dev, float *out_r_dev, void *workspace_dev, int64_t workspace_bytes,
+                     void *stream);
+
+/* ---- spatially varying DP render (local_psf_render_fast) ------------------------------------------
+ * img[B,C,H,W] float32, psf[B,H,W,2,ks,ks] (psf_is_half: 0 = float32, 1 = float16), outputs [B,C,H,W]
+ * float32.  Products and the final sum are rounded to float16 exactly as the reference's half() path.
+ * tone: 0 = none; 1 = degamma the input and gamma + clip(0,1) the output (PSFNet.render, psfnet.py:706-713). */
+int sdirt_render_local_psf(const float *img_dev, const void *psf_dev, int psf_is_half,
+                           int B, int C, int H, int W, int ks, int tone,
+                           float *out_l_dev, float *out_r_dev, void *stream);
+
+/* ---- measurement helper: dependent-free FP32 FMA loop, returns nothing; timed by the caller -------- */
+int sdirt_fp32_peak_probe(float *out_dev, int blocks, int threads, int iters, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDIRT_ENGINE_H */

@@ -236,14 +236,20 @@ def _poly_terms(s: SurfaceSpec):
 
 
 def _ipow(x, p):
-    """x**p for small integer p as torch evaluates it (p<=3: repeated products; else pow)."""
+    """x**p for small integer p.  torch evaluates p<=3 as float32 products and larger p with a (nearly)
+    correctly rounded pow; the latter is restated as the float64 product rounded once, which equals torch's
+    result for 98 % of inputs (measured) and is exactly reproducible on the GPU."""
     if p == 1:
         return x
     if p == 2:
         return x * x
     if p == 3:
         return (x * x) * x
-    return np.power(x, F32(p))
+    xd = np.asarray(x, np.float64)
+    q = xd * xd * xd
+    for _ in range(p - 3):
+        q = q * xd
+    return q.astype(F32)
 
 
 def sag(s: SurfaceSpec, r2):
@@ -318,11 +324,12 @@ def _newton_eval(s, ray, t, strict):
     return ft, t - step
 
 
-def newton_intersect(s: SurfaceSpec, ray: RayBundle, max_iters: Optional[int] = None):
+def newton_intersect(s: SurfaceSpec, ray: RayBundle, max_iters=None):
     """Newton ray/sag intersection with the reference's GLOBAL loop (surfaces.py:523-586).
 
-    Returns (valid_asphere_rule, t, iterations_run).  `max_iters` (test hook) replaces the global
-    any()-driven count by a fixed number of loop evaluations.
+    Returns (valid_asphere_rule, t, iterations_run).  `max_iters`: None = the reference's bundle-global
+    any()-driven count; an int = replay exactly that many loop evaluations; "per_ray" = every ray stops as
+    soon as its own residual is within the loose tolerance (the engine's fast path).
     """
     t0 = (s.d - ray.oz) / ray.dz
     t = t0
@@ -330,13 +337,18 @@ def newton_intersect(s: SurfaceSpec, ray: RayBundle, max_iters: Optional[int] = 
     it = 0
     with np.errstate(all="ignore"):
         while True:
-            if max_iters is None:
-                if not ((np.abs(ft) > F32(NEWTON_TOL_LOOSE)).any() and it < NEWTON_MAXITER):
+            active = np.abs(ft) > F32(NEWTON_TOL_LOOSE)
+            if max_iters is None or max_iters == "per_ray":
+                if not (active.any() and it < NEWTON_MAXITER):
                     break
             elif it >= max_iters:
                 break
             it += 1
-            ft, t = _newton_eval(s, ray, t, strict=False)
+            ft_new, t_new = _newton_eval(s, ray, t, strict=False)
+            if max_iters == "per_ray":
+                ft, t = np.where(active, ft_new, ft), np.where(active, t_new, t)
+            else:
+                ft, t = ft_new, t_new
             if np.isnan(ft).any():
                 raise FloatingPointError("nan in Newton residual")
         t = t0 + (t - t0)
@@ -387,7 +399,7 @@ def refract(s: SurfaceSpec, ray: RayBundle, eta: float, forward: bool):
     ray.ra = ray.ra * valid.astype(F32)
 
 
-def surface_step(s: SurfaceSpec, ray: RayBundle, max_iters: Optional[int] = None) -> int:
+def surface_step(s: SurfaceSpec, ray: RayBundle, max_iters=None) -> int:
     """One surface: intersect, mask, refract (surfaces.py:391-520).  In place; returns Newton iterations."""
     forward = bool((ray.dz * ray.ra).sum() > 0)          # global direction test, surfaces.py:399
     n1, n2 = refractive_index(s.mat1, ray.wvln), refractive_index(s.mat2, ray.wvln)
@@ -418,8 +430,9 @@ def trace(lens: Lens, ray: RayBundle, lens_range: Optional[Sequence[int]] = None
           newton_iters: Optional[Sequence[Optional[int]]] = None) -> List[int]:
     """Sequential trace, direction decided by the first ray's d_z (optics.py:601-689).  In place.
 
-    `record`, if a list, receives a RayBundle copy after every surface.  Returns the Newton loop
-    counts per visited surface.
+    `record`, if a list, receives a RayBundle copy after every surface.  `newton_iters`: None (global
+    loop), "per_ray", or loop counts indexed by LENS surface index.  Returns the Newton loop counts per
+    visited surface.
     """
     is_forward = bool(ray.dz.reshape(-1)[0] > 0)
     idx = list(range(len(lens.surfaces))) if lens_range is None else list(lens_range)
@@ -427,7 +440,7 @@ def trace(lens: Lens, ray: RayBundle, lens_range: Optional[Sequence[int]] = None
         idx = idx[::-1]
     counts = []
     for j, i in enumerate(idx):
-        mi = None if newton_iters is None else newton_iters[j]
+        mi = newton_iters if (newton_iters is None or isinstance(newton_iters, str)) else newton_iters[i]
         counts.append(surface_step(lens.surfaces[i], ray, mi))
         if record is not None:
             record.append(ray.copy())
@@ -442,8 +455,8 @@ def propagate_to_z(ray: RayBundle, z: float):
     ray.oz = ray.oz + ray.dz * t
 
 
-def trace_to_sensor(lens: Lens, ray: RayBundle, record=None):
-    counts = trace(lens, ray, record=record)
+def trace_to_sensor(lens: Lens, ray: RayBundle, record=None, newton_iters=None):
+    counts = trace(lens, ray, record=record, newton_iters=newton_iters)
     propagate_to_z(ray, lens.d_sensor)
     return counts
 
@@ -694,17 +707,17 @@ def sum_normalise(psf):
 
 
 def psf_bank(lens: Lens, points_obj, px, py, pupil_z, ks, wvln=DEFAULT_WAVE, centre=None,
-             centre_samples=None, params=None, normalise=True):
+             centre_samples=None, params=None, normalise=True, newton_iters=None):
     """psf_diff restated on explicit samples (optics.py:934-996).
 
     points_obj: [N,3] object-space mm.  (px, py): main pupil samples.  `centre` [N,2] or, if None,
     `centre_samples=(cx, cy)` pupil samples of the 0.25x chief-ray bundle.  Returns (L, R, centre).
     """
     ray = rays_from_points(points_obj, px, py, pupil_z, wvln)
-    trace_to_sensor(lens, ray)
+    trace_to_sensor(lens, ray, newton_iters=newton_iters)
     if centre is None:
         cray = rays_from_points(points_obj, centre_samples[0], centre_samples[1], pupil_z, DEFAULT_WAVE)
-        trace_to_sensor(lens, cray)
+        trace_to_sensor(lens, cray, newton_iters=newton_iters)
         centre = chief_ray_centre(cray)
     L, R = splat_points(ray, lens.pixel_size, ks, centre, params)
     if normalise:

@@ -1,0 +1,241 @@
+"""ctypes binding of libsdirt_engine.so (include/sdirt_engine.h).  No CPU fallback: every compute entry point
+requires CUDA tensors and raises if the library or the device is missing."""
+import ctypes as C
+import os
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libsdirt_engine.so")
+MAX_SURFACES, MAX_AI, MAX_POINTS_PER_CALL = 32, 8, 65535
+SURF_FLAT, SURF_SPHERE, SURF_ASPHERE = 0, 1, 2
+
+
+class Surface(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_ai", C.c_int32), ("square", C.c_int32), ("reserved", C.c_int32),
+                ("r", C.c_double), ("d", C.c_float), ("c", C.c_float), ("k", C.c_float),
+                ("ai", C.c_float * MAX_AI),
+                ("n1_A", C.c_double), ("n1_B", C.c_double), ("n2_A", C.c_double), ("n2_B", C.c_double)]
+
+
+class Newton(C.Structure):
+    _fields_ = [("per_ray", C.c_int32), ("iters", C.c_int32 * MAX_SURFACES)]
+
+
+class DPParams(C.Structure):
+    _fields_ = [("h", C.c_float), ("f", C.c_float), ("w", C.c_float), ("r", C.c_float)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the engine; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(f"{_LIB_PATH} is missing: run `python -m sdirt_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(_LIB_PATH)
+    vp, i64, dbl, cint = C.c_void_p, C.c_int64, C.c_double, C.c_int
+    L.sdirt_last_error.restype = C.c_char_p
+    L.sdirt_version.restype = C.c_char_p
+    L.sdirt_launch_count.restype = C.c_uint64
+    L.sdirt_device_sm_count.restype = cint
+    L.sdirt_lens_create.argtypes = [C.POINTER(Surface), cint, dbl, C.POINTER(vp)]
+    L.sdirt_lens_set_sensor.argtypes = [vp, dbl]
+    L.sdirt_lens_set_surface.argtypes = [vp, cint, C.POINTER(Surface)]
+    L.sdirt_lens_num_surfaces.argtypes = [vp]
+    L.sdirt_lens_eta.argtypes = [vp, dbl, cint, C.POINTER(dbl)]
+    L.sdirt_lens_destroy.argtypes = [vp]
+    L.sdirt_lens_destroy.restype = None
+    L.sdirt_trace_rays.argtypes = [vp, dbl, vp, vp, vp, i64, cint, cint, cint, cint, C.POINTER(Newton), vp, vp]
+    L.sdirt_psf_centre.argtypes = [vp, dbl, vp, i64, vp, i64, dbl, C.POINTER(Newton), vp, vp]
+    L.sdirt_psf_bank_workspace.argtypes = [i64, i64, cint]
+    L.sdirt_psf_bank_workspace.restype = i64
+    L.sdirt_psf_bank.argtypes = [vp, dbl, vp, i64, vp, i64, dbl, vp, cint, dbl, C.POINTER(DPParams), C.POINTER(Newton),
+                                 cint, vp, vp, vp, vp, i64, vp]
+    L.sdirt_splat_rays.argtypes = [vp, vp, vp, i64, i64, vp, cint, dbl, C.POINTER(DPParams), vp, vp, vp, i64, vp]
+    L.sdirt_render_local_psf.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
+    L.sdirt_fp32_peak_probe.argtypes = [vp, cint, cint, cint, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("sdirt_engine: " + lib().sdirt_last_error().decode())
+
+
+def version():
+    return lib().sdirt_version().decode()
+
+
+def launch_count():
+    return int(lib().sdirt_launch_count())
+
+
+def _dev(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"sdirt_engine: `{name}` must be a CUDA tensor (the engine has no CPU path)")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError(f"sdirt_engine: `{name}` must be contiguous {dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def make_surface(kind, r, d, c=0.0, k=0.0, ai=None, n1=(1.0, 0.0), n2=(1.0, 0.0), square=False):
+    s = Surface()
+    s.kind, s.square, s.r, s.d, s.c, s.k = kind, int(bool(square)), float(r), float(d), float(c), float(k)
+    ai = [] if ai is None else list(ai)
+    if len(ai) > MAX_AI:
+        raise ValueError(f"at most {MAX_AI} even-asphere coefficients")
+    s.n_ai = len(ai)
+    for i, a in enumerate(ai):
+        s.ai[i] = float(a)
+    s.n1_A, s.n1_B, s.n2_A, s.n2_B = float(n1[0]), float(n1[1]), float(n2[0]), float(n2[1])
+    return s
+
+
+def make_newton(newton):
+    """None / 'per_ray' -> per-ray loop; a sequence of ints -> replay those loop counts per lens surface."""
+    n = Newton()
+    if newton is None or (isinstance(newton, str) and newton == "per_ray"):
+        n.per_ray = 1
+    else:
+        n.per_ray = 0
+        for i, v in enumerate(newton):
+            n.iters[i] = int(v)
+    return n
+
+
+def make_dp(dp):
+    if dp is None:
+        return None
+    p = DPParams()
+    p.h, p.f, p.w, p.r = (float(v) for v in dp[:4])
+    return p
+
+
+class LensHandle:
+    """Owns one sdirt_lens*; mirrors the geometric state of a Lensgroup."""
+
+    def __init__(self, surfaces, d_sensor):
+        arr = (Surface * len(surfaces))(*surfaces)
+        h = C.c_void_p()
+        _check(lib().sdirt_lens_create(arr, len(surfaces), float(d_sensor), C.byref(h)))
+        self._h, self.n = h, len(surfaces)
+
+    def set_sensor(self, d_sensor):
+        _check(lib().sdirt_lens_set_sensor(self._h, float(d_sensor)))
+
+    def set_surface(self, i, surf):
+        _check(lib().sdirt_lens_set_surface(self._h, int(i), C.byref(surf)))
+
+    def eta(self, wvln, backward=False):
+        out = (C.c_double * self.n)()
+        _check(lib().sdirt_lens_eta(self._h, float(wvln), int(backward), out))
+        return list(out)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sdirt_lens_destroy(self._h)
+            self._h = None
+
+
+def trace_rays(lens, wvln, o, d, ra, s_begin=0, s_end=None, backward=False, to_sensor=False, newton=None, record=False):
+    """In-place trace of AoS rays o[n,3], d[n,3], ra[n]; returns the per-surface record if requested."""
+    n = ra.numel()
+    s_end = lens.n if s_end is None else s_end
+    rec = torch.empty((max(s_end - s_begin, 0), n, 7), device=o.device, dtype=torch.float32) if record else None
+    nt = make_newton(newton)
+    _check(lib().sdirt_trace_rays(lens._h, float(wvln), _dev(o, "o"), _dev(d, "d"), _dev(ra, "ra"), n, s_begin, s_end,
+                                  int(backward), int(to_sensor), C.byref(nt),
+                                  _dev(rec, "record") if record else None, _stream(o)))
+    return rec
+
+
+def psf_centre(lens, wvln, points, pupil_xy, pupil_z, newton=None):
+    n = points.shape[0]
+    out = torch.empty((n, 2), device=points.device, dtype=torch.float32)
+    nt = make_newton(newton)
+    for a in range(0, n, MAX_POINTS_PER_CALL * 1024):
+        pts = points[a:a + MAX_POINTS_PER_CALL * 1024]
+        _check(lib().sdirt_psf_centre(lens._h, float(wvln), _dev(pts, "points"), pts.shape[0], _dev(pupil_xy, "pupil_xy"),
+                                      pupil_xy.shape[0], float(pupil_z), C.byref(nt),
+                                      C.c_void_p(out[a:].data_ptr()), _stream(points)))
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), device=device, dtype=torch.uint8)
+        _ws_cache[key] = ws
+    return ws
+
+
+def psf_bank(lens, wvln, points, pupil_xy, pupil_z, centre, ks, pixel_size, dp=None, newton=None, normalise=1,
+             want_counts=False):
+    """Fused trace + DP splat.  Returns (L [N,ks,ks], R [N,ks,ks][, valid_count [N]])."""
+    n, m = points.shape[0], pupil_xy.shape[0]
+    dev = points.device
+    out_l = torch.empty((n, ks, ks), device=dev, dtype=torch.float32)
+    out_r = torch.empty((n, ks, ks), device=dev, dtype=torch.float32)
+    cnt = torch.empty((n,), device=dev, dtype=torch.int64) if want_counts else None
+    nt, dpp = make_newton(newton), make_dp(dp)
+    for a in range(0, n, MAX_POINTS_PER_CALL):
+        b = min(a + MAX_POINTS_PER_CALL, n)
+        nbytes = lib().sdirt_psf_bank_workspace(b - a, m, ks)
+        ws = _workspace(dev, nbytes)
+        _check(lib().sdirt_psf_bank(lens._h, float(wvln), _dev(points[a:b], "points"), b - a, _dev(pupil_xy, "pupil_xy"), m,
+                                    float(pupil_z), _dev(centre[a:b], "centre"), int(ks), float(pixel_size),
+                                    C.byref(dpp) if dpp is not None else None, C.byref(nt), int(normalise),
+                                    C.c_void_p(out_l[a:].data_ptr()), C.c_void_p(out_r[a:].data_ptr()),
+                                    C.c_void_p(cnt[a:].data_ptr()) if want_counts else None,
+                                    C.c_void_p(ws.data_ptr()), ws.numel(), _stream(points)))
+    return (out_l, out_r, cnt) if want_counts else (out_l, out_r)
+
+
+def splat_rays(o, d, ra, centre, ks, pixel_size, dp=None):
+    """forward_integral on an existing [spp,N] Ray: returns raw (L, R) [N,ks,ks]."""
+    m, n = ra.shape
+    dev = o.device
+    out_l = torch.empty((n, ks, ks), device=dev, dtype=torch.float32)
+    out_r = torch.empty((n, ks, ks), device=dev, dtype=torch.float32)
+    if n > MAX_POINTS_PER_CALL:
+        raise RuntimeError("sdirt_engine: split forward_integral calls above 65535 points")
+    nbytes = lib().sdirt_psf_bank_workspace(n, m, ks) + 8 * n
+    ws = _workspace(dev, nbytes)
+    dpp = make_dp(dp)
+    _check(lib().sdirt_splat_rays(_dev(o, "o"), _dev(d, "d"), _dev(ra, "ra"), m, n,
+                                  _dev(centre, "centre") if centre is not None else None, int(ks), float(pixel_size),
+                                  C.byref(dpp) if dpp is not None else None, _dev(out_l, "out_l"), _dev(out_r, "out_r"),
+                                  C.c_void_p(ws.data_ptr()), ws.numel(), _stream(o)))
+    return out_l, out_r
+
+
+def render_local_psf(img, psf, ks, tone=False):
+    """img [B,C,H,W] float32, psf [B,H,W,2,ks,ks] float32/float16 -> (rl, rr) float32."""
+    b, c, h, w = img.shape
+    if psf.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("sdirt_engine: psf must be float32 or float16")
+    if psf.numel() != b * h * w * 2 * ks * ks:
+        raise RuntimeError("sdirt_engine: psf has the wrong number of elements for [B,H,W,2,ks,ks]")
+    rl, rr = torch.empty_like(img), torch.empty_like(img)
+    _check(lib().sdirt_render_local_psf(_dev(img, "img"), _dev(psf, "psf", psf.dtype), int(psf.dtype == torch.float16),
+                                        b, c, h, w, int(ks), int(bool(tone)), _dev(rl, "out_l"), _dev(rr, "out_r"),
+                                        _stream(img)))
+    return rl, rr
+
+
+def fp32_peak_probe(device, blocks, threads, iters):
+    out = torch.empty(blocks * threads, device=device, dtype=torch.float32)
+    _check(lib().sdirt_fp32_peak_probe(_dev(out, "out"), blocks, threads, iters, _stream(out)))
+    return out
