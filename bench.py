@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — rays/s traced + splatted into dual-pixel PSFs (BASELINE.json metric), one JSON line.
+
+Workload (BASELINE.json configs[1]): the rf50mm F/4 PSF bank for PSFNet fitting, 64x64 field points x 32 depths,
+2 M rays per point.  One "step" = one depth slab of that bank: 4096 points x 2 M rays = 8.4e9 rays through
+sample -> 12-surface trace -> DP weights -> bilinear splat -> normalise, i.e. 4096 (L, R) PSF pairs.  Consecutive
+steps take consecutive depth slabs.  With N GPUs every rank works on its own slab (weak scaling, no collective on
+the data path); `value` is the whole-job rays/s = N x slab rays / max-over-ranks device time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--numerics strict|hybrid|fast] [--impl reference]
+
+`--impl reference` times the CPU restatement of the reference's own algorithm (oracle/dp_oracle.py, all host
+cores) on bounded samples of the same workload and prints the same JSON shape with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID, DEPTHS, SPP, KS = 64, 32, 2_000_000, 21
+SENSOR_RES = (512, 768)
+LENS = "rf50mm"
+FLOP_PER_RAY = 2.1e3     # algorithmic flop/ray, rf50mm, per-ray Newton counts (FMA = 2)
+# Derived once with the engine on a B200 (tests/test_api_gpu.py pins them against the reference's values):
+HFOV = {"rf50mm": 0.40959781408309937}
+PUPIL = {"rf50mm": (22.51324462890625, 6.019352912902832)}
+D_SENSOR = {"rf50mm": 62.25}
+
+
+# ----------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------
+def bank_points(slab):
+    """Normalised (x, y, depth) of depth slab `slab` (0..31): cell-centred 64x64 field grid (psfnet.py:221-225 with
+    64 cells) at the slab's depth, z from the get_test_data warp of linspace(-3, 3, 32) (psfnet.py:229-232)."""
+    import torch
+    g = GRID
+    x, y = torch.meshgrid(torch.linspace(-1 + 1 / (2 * g), 1 - 1 / (2 * g), g),
+                          torch.linspace(1 - 1 / (2 * g), -1 + 1 / (2 * g), g), indexing="xy")
+    d_min, d_max, ds = -200.0, -20000.0, D_SENSOR[LENS]
+    foc_z = ((-1000.0 + ds) - d_min) / (d_max - d_min)
+    zg = torch.linspace(-3, 3, DEPTHS)[slab % DEPTHS]
+    z = (1 - foc_z) * zg / 3 + foc_z if zg > 0 else foc_z * zg / 3 + foc_z
+    depth = z * (d_max - d_min) + d_min
+    return torch.stack((x.reshape(-1), y.reshape(-1), torch.full((g * g,), float(depth))), -1).float()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None, "samples": len(self.rows), "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU leg: the oracle (a restatement of the reference's torch-CPU algorithm) on all host cores
+# ----------------------------------------------------------------------------------------------------
+def _cpu_chunk(args):
+    """Worker: trace + splat `n_pts` points x one chunk of pupil samples with the numpy oracle."""
+    slab, p0, n_pts, seed, spp = args
+    from oracle import dp_oracle as O
+    lens = O.load_lens(os.path.join(ROOT, "sdirt_b200", "lenses", LENS + ".json"), sensor_res=SENSOR_RES, d_sensor=D_SENSOR[LENS])
+    lens.hfov = HFOV[LENS]
+    pts = O.object_points(lens, bank_points(slab).numpy()[p0:p0 + n_pts])
+    rng = np.random.default_rng(seed)
+    pz, pr = PUPIL[LENS]
+    px, py = O.pupil_points(rng.random(spp, dtype=np.float32), rng.random(spp, dtype=np.float32), pr)
+    cx, cy = O.pupil_points(rng.random(2048, dtype=np.float32), rng.random(2048, dtype=np.float32), pr * 0.25)
+    L, R, _ = O.psf_bank(lens, pts, px, py, pz, KS, centre_samples=(cx, cy), params=O.DP_DEFAULT)
+    return float(L.sum() + R.sum())
+
+
+def cpu_rays_per_s(n_pts, spp, repeats=1, slab0=0):
+    """Time the oracle on `n_pts` points x `spp` rays per repeat, points spread over all host cores."""
+    from concurrent.futures import ProcessPoolExecutor
+    cores = os.cpu_count() or 1
+    per = max(1, n_pts // cores)
+    times = []
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(_cpu_chunk, [(0, 0, 1, 0, 256)] * cores))            # spin the workers up (imports)
+        for r in range(repeats):
+            jobs = [(slab0 + r, p0, min(per, n_pts - p0), 1000 + r, spp) for p0 in range(0, n_pts, per)]
+            t0 = time.perf_counter()
+            list(ex.map(_cpu_chunk, jobs))
+            times.append(time.perf_counter() - t0)
+    return [n_pts * spp / t for t in times], times, cores
+
+
+def run_reference(args):
+    """`--impl reference`: K timed steps, each a bounded sample (64 points x 32768 rays) of the slab workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_pts, spp = 64, 131072
+    rates, times, cores = cpu_rays_per_s(n_pts, spp, repeats=args.warmup + args.steps, slab0=0)
+    rates, times = rates[args.warmup:], times[args.warmup:]
+    value = n_pts * spp * len(times) / sum(times)
+    sample = f"{n_pts} points x {spp} rays per step of the {GRID}x{GRID}x{DEPTHS} x 2M-ray bank"
+    print(json.dumps({
+        "impl": "reference", "metric": "rays/sec traced+splatted into DP L/R PSFs", "value": value, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config("cpu"),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "dp_psfs_per_s": value / spp,
+    }))
+
+
+def workload_config(numerics):
+    return {"workload": f"{LENS} F/4 PSF bank, {GRID}x{GRID} field x {DEPTHS} depths, {SPP} rays/point, ks={KS}, "
+                        f"sensor {SENSOR_RES[0]}x{SENSOR_RES[1]}; step = one depth slab ({GRID * GRID} points)",
+            "lens": LENS, "points_per_step": GRID * GRID, "rays_per_point": SPP, "ks": KS, "numerics": numerics,
+            "l2": "L2 flushed (256 MiB write) between timed steps; the 16 MB shared pupil-sample set is re-read from L2 "
+                  "by every point inside a step by design"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU leg
+# ----------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from sdirt_b200 import _engine as E, lens_file
+    from sdirt_b200.deeplens import PSFNet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU leg)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lens = PSFNet(lens_file(LENS), sensor_res=SENSOR_RES, kernel_size=KS, device=dev)
+    lens.numerics = args.numerics
+    handle = lens._engine_lens()
+    pz, pr = lens.entrance_pupil()
+
+    # ---- device-resident inputs for the kernel-only number ------------------------------------------
+    torch.manual_seed(1234)                                        # same pupil samples on every rank (optics.py:483-490)
+    theta = torch.rand(SPP) * 2 * np.pi
+    rho = torch.sqrt(torch.rand(SPP) * pr ** 2)
+    pupil = torch.stack((rho * torch.cos(theta), rho * torch.sin(theta)), 1).to(dev).contiguous()
+    cpupil = (pupil[:2048] * 0.25).contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    total_steps = args.warmup + args.steps
+    slabs = [lens._object_points(bank_points((s * world + rank))).to(dev).contiguous() for s in range(total_steps)]
+    centres = [E.psf_centre(handle, 0.589, p, cpupil, pz, numerics=args.numerics) for p in slabs]
+    n_pts = slabs[0].shape[0]
+
+    def step(i):
+        return E.psf_bank(handle, 0.589, slabs[i], pupil, pz, centres[i], KS, lens.pixel_size, numerics=args.numerics)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = E.launch_count()
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        out = step(args.warmup + k)
+        ev[k][1].record()
+    barrier()
+    launches = E.launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    rays_per_step = n_pts * SPP
+    value = world * rays_per_step * args.steps / (total_ms * 1e-3)
+    assert torch.isfinite(out[0]).all() and float(out[0].max()) > 0.99
+
+    # ---- end to end through the public API, host buffers in, host buffers out -------------------------
+    pinned_out = torch.empty((n_pts, 2, KS, KS), dtype=torch.float32).pin_memory()
+    e2e_steps = max(2, min(args.steps, 4))
+    host_pts = [bank_points(s * world + rank) for s in range(e2e_steps + 1)]
+
+    def e2e_step(i):
+        torch.manual_seed(99 + i)
+        L, R = lens.psf_dp(host_pts[i], ks=KS, spp=SPP)           # CPU sampling + H2D + centre + bank kernels
+        pinned_out[:, 0].copy_(L, non_blocking=True)
+        pinned_out[:, 1].copy_(R, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(1, e2e_steps + 1):
+        e2e_step(i)
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * rays_per_step * e2e_steps / float(e2e_t.item())
+    h2d = SPP * 2 * 4 + 2048 * 2 * 4 + n_pts * 3 * 4
+    d2h = n_pts * 2 * KS * KS * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (psf_bank_kernel): FP32 pipe --------------------------------
+    blocks, threads, iters = 148 * 8, 256, 1 << 15
+    E.fp32_peak_probe(dev, blocks, threads, 2048)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    E.fp32_peak_probe(dev, blocks, threads, iters)
+    b.record()
+    torch.cuda.synchronize()
+    fp32_peak = blocks * threads * iters * 16.0 / (a.elapsed_time(b) * 1e-3) / 1e12
+    per_gpu_rate = rays_per_step * args.steps / (sum(step_ms) * 1e-3)
+    achieved = FLOP_PER_RAY * per_gpu_rate / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                "traffic": None,
+                "note": "psf_bank_kernel is FP32-issue bound, not HBM/tensor bound; peak = FFMA micro-benchmark measured in "
+                        "this run (MEASURED_PEAKS.json has no fp32 entry; its hbm_gbs=%s). achieved = %.0f flop/ray "
+                        "(SURVEY 8d) x rays/s of the kernel alone. HBM traffic per launch is ~30 MB (ncu, profiles/)."
+                        % (peaks.get("hbm_gbs"), FLOP_PER_RAY)}
+
+    # ---- CPU baseline on this box's host cores (bounded sample) --------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        rates, times, cores = cpu_rays_per_s(64, 131072, repeats=2)
+        cpu = {"value": rates[-1], "unit": "rays/s", "cores": cores, "kind": "port",
+               "sample": "64 points x 131072 rays of depth slab 1 (oracle/dp_oracle.py, numpy, one process per core)"}
+
+    print(json.dumps({
+        "metric": "rays/sec traced+splatted into DP L/R PSFs", "value": value, "unit": "rays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.numerics),
+        "dp_psfs_per_s": value / SPP,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "PSFNet.psf_dp(host points) -> pinned host (L, R)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sdirt_b200", choices=["sdirt_b200", "reference"])
+    ap.add_argument("--numerics", default="hybrid", choices=["strict", "hybrid", "fast"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

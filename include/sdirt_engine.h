@@ -12,6 +12,9 @@
  *                                      Aspheric.ray_reaction               deeplens/surfaces.py:391-520
  *                                      Aspheric._newtons_method/_refract   deeplens/surfaces.py:523-679
  *                                      Ray.propagate_to                    deeplens/basics.py:256-264
+ *   sdirt_sample_rays               <- Lensgroup.sample_from_points        deeplens/optics.py:460-494
+ *   sdirt_normalize_rays            <- Ray.__init__ (F.normalize)          deeplens/basics.py:245
+ *   sdirt_propagate_rays            <- Ray.propagate_to                    deeplens/basics.py:256-264
  *   sdirt_psf_centre                <- Lensgroup.psf_center('chief_ray')   deeplens/optics.py:889-904
  *   sdirt_psf_bank                  <- Lensgroup.psf_diff                  deeplens/optics.py:934-996
  *                                      sample_from_points                  deeplens/optics.py:476-494
@@ -68,15 +71,31 @@ typedef struct sdirt_surface {
 
 typedef struct sdirt_lens sdirt_lens;   /* opaque */
 
-/* Newton iteration control (surfaces.py:543-561).
- *   per_ray = 1: each ray leaves the loose loop as soon as ITS residual is <= 50e-6 mm (fast path).
- *   per_ray = 0: replay fixed loop counts, iters[i] loop evaluations at surface i of the lens (this
- *                reproduces the reference's bundle-global `while any()` count when the caller knows it).
- * Both are followed by the reference's one extra strict evaluation. */
-typedef struct sdirt_newton {
-    int32_t per_ray;
+/* Trace options.
+ *
+ * newton_mode (surfaces.py:543-561, the loose Newton loop):
+ *   SDIRT_NEWTON_PER_RAY  each ray leaves the loop as soon as ITS residual is <= 50e-6 mm;
+ *   SDIRT_NEWTON_REPLAY   replay fixed loop counts, iters[i] loop evaluations at lens surface i (this
+ *                         reproduces the reference's bundle-global `while any()` count when the caller
+ *                         knows it).  Both are followed by the reference's one extra strict evaluation.
+ * numerics:
+ *   SDIRT_NUMERICS_STRICT float32 in the reference's exact operation order, IEEE add/mul/div/sqrt, no FMA
+ *                         contraction: bit-identical to oracle/dp_oracle.py (the verification mode);
+ *   SDIRT_NUMERICS_FAST   same geometry, B200-shaped arithmetic: closed-form ray/sphere intersection from
+ *                         the vertex plane, FMA, Newton (from the vertex plane, step-converged) only on
+ *                         conic/aspheric surfaces.  Agrees with STRICT to float32 rounding noise; see
+ *                         DESIGN.md for the measured parity.  newton_mode / iters are ignored;
+ *   SDIRT_NUMERICS_HYBRID FAST, except that the first visited surface is traced with the STRICT arithmetic.
+ *                         For distant objects the reference's first hit carries up to ~1e-3 mm of float32
+ *                         cancellation noise (t ~ 2e3..2e4 mm); reproducing it bit-for-bit is what keeps the
+ *                         sensor-pixel assignment identical to the reference's for >= 99.99 % of rays. */
+enum { SDIRT_NEWTON_REPLAY = 0, SDIRT_NEWTON_PER_RAY = 1 };
+enum { SDIRT_NUMERICS_STRICT = 0, SDIRT_NUMERICS_FAST = 1, SDIRT_NUMERICS_HYBRID = 2 };
+typedef struct sdirt_options {
+    int32_t newton_mode;
+    int32_t numerics;
     int32_t iters[SDIRT_MAX_SURFACES];
-} sdirt_newton;
+} sdirt_options;
 
 /* Dual-pixel sub-aperture model (monte_carlo.py:157-164), pixel units. */
 typedef struct sdirt_dp_params {
@@ -107,7 +126,19 @@ void sdirt_lens_destroy(sdirt_lens *lens);
 int sdirt_trace_rays(const sdirt_lens *lens, double wvln_um,
                      float *o_dev, float *d_dev, float *ra_dev, int64_t n,
                      int s_begin, int s_end, int backward, int to_sensor,
-                     const sdirt_newton *newton, float *record_dev, void *stream);
+                     const sdirt_options *opts, float *record_dev, void *stream);
+
+/* ---- ray bundle of sample_from_points (optics.py:476-494, basics.py:233-245) ----------------------
+ * o_out, d_out: [m, N, 3] sample-major AoS, d = normalize(pupil_j - point_i).  Compatibility path for callers
+ * that want a Ray object; sdirt_psf_bank never materialises rays. */
+int sdirt_sample_rays(const float *points_dev, int64_t n_points, const float *pupil_xy_dev, int64_t n_samples,
+                      double pupil_z, float *o_out_dev, float *d_out_dev, void *stream);
+
+/* ---- Ray.__init__ normalisation (basics.py:245): d /= max(|d|, 1e-12), in place on AoS directions - */
+int sdirt_normalize_rays(float *d_dev, int64_t n, void *stream);
+
+/* ---- Ray.propagate_to(z) (basics.py:256-264): o += d * (z - o_z) / d_z, in place on AoS rays ------- */
+int sdirt_propagate_rays(float *o_dev, const float *d_dev, int64_t n, double z, void *stream);
 
 /* ---- chief-ray PSF centre (Lensgroup.psf_center) --------------------------------------------------
  * points[N,3] object-space mm; pupil_xy[m,2] samples on the (shrunken) entrance pupil at z = pupil_z,
@@ -115,7 +146,7 @@ int sdirt_trace_rays(const sdirt_lens *lens, double wvln_um,
 int sdirt_psf_centre(const sdirt_lens *lens, double wvln_um,
                      const float *points_dev, int64_t n_points,
                      const float *pupil_xy_dev, int64_t n_samples, double pupil_z,
-                     const sdirt_newton *newton, float *centre_out_dev, void *stream);
+                     const sdirt_options *opts, float *centre_out_dev, void *stream);
 
 /* ---- fused sample -> trace -> DP weights -> splat -> normalise (Lensgroup.psf_diff) ---------------
  * For every point i and pupil sample j a ray from points[i] towards (pupil_xy[j], pupil_z) is traced to
@@ -129,7 +160,7 @@ int sdirt_psf_bank(const sdirt_lens *lens, double wvln_um,
                    const float *points_dev, int64_t n_points,
                    const float *pupil_xy_dev, int64_t n_samples, double pupil_z,
                    const float *centre_dev, int ks, double pixel_size,
-                   const sdirt_dp_params *dp, const sdirt_newton *newton, int normalise,
+                   const sdirt_dp_params *dp, const sdirt_options *opts, int normalise,
                    float *out_l_dev, float *out_r_dev, int64_t *valid_count_dev,
                    void *workspace_dev, int64_t workspace_bytes, void *stream);
 
@@ -145,7 +176,8 @@ int sdirt_splat_rays(const float *o_dev, const float *d_dev, const float *ra_dev
 /* ---- spatially varying DP render (local_psf_render_fast) ------------------------------------------
  * img[B,C,H,W] float32, psf[B,H,W,2,ks,ks] (psf_is_half: 0 = float32, 1 = float16), outputs [B,C,H,W]
  * float32.  Products and the final sum are rounded to float16 exactly as the reference's half() path.
- * tone: 0 = none; 1 = degamma the input and gamma + clip(0,1) the output (PSFNet.render, psfnet.py:706-713). */
+ * tone (bit mask): 1 = degamma the input (psfnet.py:589-603, :706); 2 = gamma + clip(0,1) on the output
+ * (psfnet.py:605-620, :708-713).  PSFNet.render(train=False) is tone = 3. */
 int sdirt_render_local_psf(const float *img_dev, const void *psf_dev, int psf_is_half,
                            int B, int C, int H, int W, int ks, int tone,
                            float *out_l_dev, float *out_r_dev, void *stream);

@@ -60,6 +60,22 @@ DP_DEFAULT = (0.78, 1.44, 0.3, 0.5, "l")   # (h, f, w, r, direct)  monte_carlo.p
 # ------------------------------------------------------------------------------------------------
 # float32 helpers
 # ------------------------------------------------------------------------------------------------
+class precision:
+    """`with precision(np.float64):` re-runs the same restatement in float64 (the arbiter used to show which of
+    two float32 results is closer to the exact geometry).  Not thread-safe; tests only."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global F32
+        self.prev, F32 = F32, self.dtype
+
+    def __exit__(self, *exc):
+        global F32
+        F32 = self.prev
+
+
 def _f(x):
     return np.asarray(x, dtype=F32)
 
@@ -67,6 +83,7 @@ def _f(x):
 def _fma(a, b, c):
     """float32 fused multiply-add emulated through float64 (exact product, one final rounding)."""
     return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(F32)
+
 
 
 def _norm3(x, y, z):

@@ -17,8 +17,13 @@ class Surface(C.Structure):
                 ("n1_A", C.c_double), ("n1_B", C.c_double), ("n2_A", C.c_double), ("n2_B", C.c_double)]
 
 
-class Newton(C.Structure):
-    _fields_ = [("per_ray", C.c_int32), ("iters", C.c_int32 * MAX_SURFACES)]
+class Options(C.Structure):
+    _fields_ = [("newton_mode", C.c_int32), ("numerics", C.c_int32), ("iters", C.c_int32 * MAX_SURFACES)]
+
+
+NEWTON_REPLAY, NEWTON_PER_RAY = 0, 1
+NUMERICS_STRICT, NUMERICS_FAST, NUMERICS_HYBRID = 0, 1, 2
+DEFAULT_NUMERICS = NUMERICS_STRICT
 
 
 class DPParams(C.Structure):
@@ -48,11 +53,14 @@ def lib():
     L.sdirt_lens_eta.argtypes = [vp, dbl, cint, C.POINTER(dbl)]
     L.sdirt_lens_destroy.argtypes = [vp]
     L.sdirt_lens_destroy.restype = None
-    L.sdirt_trace_rays.argtypes = [vp, dbl, vp, vp, vp, i64, cint, cint, cint, cint, C.POINTER(Newton), vp, vp]
-    L.sdirt_psf_centre.argtypes = [vp, dbl, vp, i64, vp, i64, dbl, C.POINTER(Newton), vp, vp]
+    L.sdirt_trace_rays.argtypes = [vp, dbl, vp, vp, vp, i64, cint, cint, cint, cint, C.POINTER(Options), vp, vp]
+    L.sdirt_sample_rays.argtypes = [vp, i64, vp, i64, dbl, vp, vp, vp]
+    L.sdirt_normalize_rays.argtypes = [vp, i64, vp]
+    L.sdirt_propagate_rays.argtypes = [vp, vp, i64, dbl, vp]
+    L.sdirt_psf_centre.argtypes = [vp, dbl, vp, i64, vp, i64, dbl, C.POINTER(Options), vp, vp]
     L.sdirt_psf_bank_workspace.argtypes = [i64, i64, cint]
     L.sdirt_psf_bank_workspace.restype = i64
-    L.sdirt_psf_bank.argtypes = [vp, dbl, vp, i64, vp, i64, dbl, vp, cint, dbl, C.POINTER(DPParams), C.POINTER(Newton),
+    L.sdirt_psf_bank.argtypes = [vp, dbl, vp, i64, vp, i64, dbl, vp, cint, dbl, C.POINTER(DPParams), C.POINTER(Options),
                                  cint, vp, vp, vp, vp, i64, vp]
     L.sdirt_splat_rays.argtypes = [vp, vp, vp, i64, i64, vp, cint, dbl, C.POINTER(DPParams), vp, vp, vp, i64, vp]
     L.sdirt_render_local_psf.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
@@ -99,15 +107,26 @@ def make_surface(kind, r, d, c=0.0, k=0.0, ai=None, n1=(1.0, 0.0), n2=(1.0, 0.0)
     return s
 
 
-def make_newton(newton):
-    """None / 'per_ray' -> per-ray loop; a sequence of ints -> replay those loop counts per lens surface."""
-    n = Newton()
+def make_options(newton=None, numerics=None):
+    """newton: None / 'per_ray' -> per-ray loop; a sequence of ints -> replay those loop counts per lens surface.
+    numerics: 'strict' (bit-exact restatement of the reference arithmetic), 'fast', or None for the default."""
+    n = Options()
     if newton is None or (isinstance(newton, str) and newton == "per_ray"):
-        n.per_ray = 1
+        n.newton_mode = NEWTON_PER_RAY
     else:
-        n.per_ray = 0
+        n.newton_mode = NEWTON_REPLAY
         for i, v in enumerate(newton):
             n.iters[i] = int(v)
+    if numerics is None:
+        n.numerics = DEFAULT_NUMERICS
+    elif numerics in ("strict", NUMERICS_STRICT):
+        n.numerics = NUMERICS_STRICT
+    elif numerics in ("fast", NUMERICS_FAST):
+        n.numerics = NUMERICS_FAST
+    elif numerics in ("hybrid", NUMERICS_HYBRID):
+        n.numerics = NUMERICS_HYBRID
+    else:
+        raise ValueError(f"numerics must be 'strict', 'hybrid' or 'fast', got {numerics!r}")
     return n
 
 
@@ -145,22 +164,40 @@ class LensHandle:
             self._h = None
 
 
-def trace_rays(lens, wvln, o, d, ra, s_begin=0, s_end=None, backward=False, to_sensor=False, newton=None, record=False):
+def trace_rays(lens, wvln, o, d, ra, s_begin=0, s_end=None, backward=False, to_sensor=False, newton=None, record=False, numerics=None):
     """In-place trace of AoS rays o[n,3], d[n,3], ra[n]; returns the per-surface record if requested."""
     n = ra.numel()
     s_end = lens.n if s_end is None else s_end
     rec = torch.empty((max(s_end - s_begin, 0), n, 7), device=o.device, dtype=torch.float32) if record else None
-    nt = make_newton(newton)
+    nt = make_options(newton, numerics)
     _check(lib().sdirt_trace_rays(lens._h, float(wvln), _dev(o, "o"), _dev(d, "d"), _dev(ra, "ra"), n, s_begin, s_end,
                                   int(backward), int(to_sensor), C.byref(nt),
                                   _dev(rec, "record") if record else None, _stream(o)))
     return rec
 
 
-def psf_centre(lens, wvln, points, pupil_xy, pupil_z, newton=None):
+def sample_rays(points, pupil_xy, pupil_z):
+    """[spp, N, 3] origins and unit directions of sample_from_points (sample-major, as the reference's Ray)."""
+    n, m = points.shape[0], pupil_xy.shape[0]
+    o = torch.empty((m, n, 3), device=points.device, dtype=torch.float32)
+    d = torch.empty((m, n, 3), device=points.device, dtype=torch.float32)
+    _check(lib().sdirt_sample_rays(_dev(points, "points"), n, _dev(pupil_xy, "pupil_xy"), m, float(pupil_z),
+                                   _dev(o, "o"), _dev(d, "d"), _stream(points)))
+    return o, d
+
+
+def normalize_rays(d):
+    _check(lib().sdirt_normalize_rays(_dev(d, "d"), d.numel() // 3, _stream(d)))
+
+
+def propagate_rays(o, d, z):
+    _check(lib().sdirt_propagate_rays(_dev(o, "o"), _dev(d, "d"), o.numel() // 3, float(z), _stream(o)))
+
+
+def psf_centre(lens, wvln, points, pupil_xy, pupil_z, newton=None, numerics=None):
     n = points.shape[0]
     out = torch.empty((n, 2), device=points.device, dtype=torch.float32)
-    nt = make_newton(newton)
+    nt = make_options(newton, numerics)
     for a in range(0, n, MAX_POINTS_PER_CALL * 1024):
         pts = points[a:a + MAX_POINTS_PER_CALL * 1024]
         _check(lib().sdirt_psf_centre(lens._h, float(wvln), _dev(pts, "points"), pts.shape[0], _dev(pupil_xy, "pupil_xy"),
@@ -182,14 +219,14 @@ def _workspace(device, nbytes):
 
 
 def psf_bank(lens, wvln, points, pupil_xy, pupil_z, centre, ks, pixel_size, dp=None, newton=None, normalise=1,
-             want_counts=False):
+             want_counts=False, numerics=None):
     """Fused trace + DP splat.  Returns (L [N,ks,ks], R [N,ks,ks][, valid_count [N]])."""
     n, m = points.shape[0], pupil_xy.shape[0]
     dev = points.device
     out_l = torch.empty((n, ks, ks), device=dev, dtype=torch.float32)
     out_r = torch.empty((n, ks, ks), device=dev, dtype=torch.float32)
     cnt = torch.empty((n,), device=dev, dtype=torch.int64) if want_counts else None
-    nt, dpp = make_newton(newton), make_dp(dp)
+    nt, dpp = make_options(newton, numerics), make_dp(dp)
     for a in range(0, n, MAX_POINTS_PER_CALL):
         b = min(a + MAX_POINTS_PER_CALL, n)
         nbytes = lib().sdirt_psf_bank_workspace(b - a, m, ks)
@@ -221,8 +258,9 @@ def splat_rays(o, d, ra, centre, ks, pixel_size, dp=None):
     return out_l, out_r
 
 
-def render_local_psf(img, psf, ks, tone=False):
-    """img [B,C,H,W] float32, psf [B,H,W,2,ks,ks] float32/float16 -> (rl, rr) float32."""
+def render_local_psf(img, psf, ks, tone=0):
+    """img [B,C,H,W] float32, psf [B,H,W,2,ks,ks] float32/float16 -> (rl, rr) float32.
+    tone bits: 1 = degamma the input, 2 = gamma + clip the output."""
     b, c, h, w = img.shape
     if psf.dtype not in (torch.float32, torch.float16):
         raise RuntimeError("sdirt_engine: psf must be float32 or float16")
@@ -230,7 +268,7 @@ def render_local_psf(img, psf, ks, tone=False):
         raise RuntimeError("sdirt_engine: psf has the wrong number of elements for [B,H,W,2,ks,ks]")
     rl, rr = torch.empty_like(img), torch.empty_like(img)
     _check(lib().sdirt_render_local_psf(_dev(img, "img"), _dev(psf, "psf", psf.dtype), int(psf.dtype == torch.float16),
-                                        b, c, h, w, int(ks), int(bool(tone)), _dev(rl, "out_l"), _dev(rr, "out_r"),
+                                        b, c, h, w, int(ks), int(tone), _dev(rl, "out_l"), _dev(rr, "out_r"),
                                         _stream(img)))
     return rl, rr
 

@@ -184,6 +184,36 @@ def golden_psf():
     np.savez_compressed(os.path.join(HERE, "psf.npz"), **out)
 
 
+def golden_psf2m():
+    """BASELINE config-2 sample count: 2 M rays per point, three points incl. the worst case for float32
+    cancellation at the first surface (field corner at 20 m)."""
+    out = {}
+    spp = 2_000_000
+    lens = make_lens("rf50mm")
+    ds = lens.d_sensor
+    pts = torch.tensor([[0, 0, -2000 + ds], [0.98, -0.98, -20000 + ds], [0.4, 0.3, -700 + ds]], dtype=torch.float32)
+    out["points_norm"] = pts.numpy()
+    out["hfov"] = np.float64(lens.hfov)
+    pz, pr = lens.entrance_pupil()
+    out["pupil"] = np.asarray([pz, pr], np.float64)
+    for tag in ("l", "r"):
+        torch.manual_seed(9)
+        u = [torch.rand(spp).numpy() for _ in range(2)] + [torch.rand(2048).numpy() for _ in range(2)]
+        torch.manual_seed(9)
+        out[tag] = lens.psf_diff(pts, ks=21, spp=spp, param_list=DP + (tag,)).numpy()
+        out["u_check"] = np.asarray([float(v.astype(np.float64).sum()) for v in u] + [spp])
+    depth = pts[:, 2]
+    scale = lens.calc_scale_pinhole(depth)
+    obj = pts.clone()
+    obj[:, 0] = pts[:, 0] * scale * lens.sensor_size[1] / 2
+    obj[:, 1] = pts[:, 1] * scale * lens.sensor_size[0] / 2
+    out["points_obj"] = obj.numpy()
+    torch.manual_seed(9)
+    torch.rand(spp), torch.rand(spp)
+    out["centre"] = lens.psf_center(obj).numpy()
+    np.savez_compressed(os.path.join(HERE, "psf2m.npz"), **out)
+
+
 def golden_render():
     torch.manual_seed(11)
     lens = make_lens("rf50mm", res=(32, 48))
@@ -224,7 +254,7 @@ def golden_render():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["setup", "trace", "dp", "psf", "render"]
+    which = sys.argv[1:] or ["setup", "trace", "dp", "psf", "psf2m", "render"]
     for w in which:
         globals()[f"golden_{w}"]()
         print("wrote", w)

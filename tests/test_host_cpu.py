@@ -1,0 +1,129 @@
+"""CPU: host logic of the product (no GPU, no compute calls): C-ABI exports, prescription IO, dispersion, options,
+sharding arithmetic and the world_size-2 gather over gloo, loud failure without CUDA."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, lens_path
+
+
+def test_build_and_exports():
+    import __graft_entry__ as ge
+    path = ge.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "sdirt_engine.h")).read()
+    names = sorted(set(re.findall(r"\b(sdirt_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.sdirt_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.sdirt_version()
+
+
+def test_sass_is_sm100a():
+    out = os.popen(f"cuobjdump -lelf {os.path.join(ROOT, 'sdirt_b200', '_lib', 'libsdirt_engine.so')} 2>/dev/null").read()
+    assert "sm_100a" in out
+
+
+def test_prescription_and_eta(golden):
+    from sdirt_b200 import _engine as E
+    from sdirt_b200.prescription import find_aperture, load_lens_json
+    g = golden("setup")
+    for name, n_surf, aper, n_asph in (("rf50mm", 12, 5, 2), ("rf35mm", 21, 7, 1)):
+        recs, descs, head = load_lens_json(lens_path(name))
+        assert len(recs) == n_surf and find_aperture(descs) == aper
+        assert sum(d["kind"] == E.SURF_ASPHERE for d in descs) == n_asph
+        assert descs[aper]["kind"] == E.SURF_FLAT
+        h = E.LensHandle(recs, head["d_sensor"])           # host-only object: no device needed
+        for wi, wv in enumerate((0.656, 0.589, 0.486)):
+            np.testing.assert_allclose(h.eta(wv), g[f"{name}_eta"][wi], rtol=1e-15)
+            np.testing.assert_allclose(h.eta(wv, backward=True), 1.0 / g[f"{name}_eta"][wi], rtol=1e-15)
+
+
+def test_bad_arguments_are_reported():
+    from sdirt_b200 import _engine as E
+    with pytest.raises(RuntimeError, match="curved surface with c == 0"):
+        E.LensHandle([E.make_surface(E.SURF_SPHERE, 5.0, 0.0, 0.0)], 10.0)
+    with pytest.raises(RuntimeError, match="surfaces"):
+        E.LensHandle([E.make_surface(E.SURF_FLAT, 5.0, float(i)) for i in range(40)], 10.0)
+    with pytest.raises(ValueError):
+        E.make_options(numerics="sloppy")
+    o = E.make_options([3, 2, 1], "hybrid")
+    assert (o.newton_mode, o.numerics, list(o.iters[:3])) == (E.NEWTON_REPLAY, E.NUMERICS_HYBRID, [3, 2, 1])
+
+
+def test_no_cpu_fallback():
+    """The product refuses CPU tensors / a CPU device instead of silently computing somewhere else."""
+    from sdirt_b200 import _engine as E, lens_file
+    from sdirt_b200.deeplens import PSFNet, local_psf_render_fast
+    from sdirt_b200.prescription import load_lens_json
+    recs, _, head = load_lens_json(lens_file("rf50mm"))
+    h = E.LensHandle(recs, 62.25)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        E.trace_rays(h, 0.589, torch.zeros(4, 3), torch.zeros(4, 3), torch.ones(4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PSFNet(lens_file("rf50mm"), sensor_res=(512, 768), kernel_size=21, device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        local_psf_render_fast(torch.rand(1, 3, 8, 8), torch.rand(1, 8, 8, 2, 5, 5), 5)
+    import sdirt_b200
+    src = "".join(open(os.path.join(ROOT, "sdirt_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "sdirt_b200")) if f.endswith(".py"))
+    assert "oracle" not in src.replace("oracle/dp_oracle.py", "")      # the product never imports the oracle
+
+
+def test_mlp_matches_reference_init(golden):
+    """Seeded construction reproduces the reference's random-init PSF MLP (checksums from the reference)."""
+    from sdirt_b200.deeplens.psfnet_arch import MLP, initialize_weights
+    g = golden("render")
+    torch.manual_seed(5)
+    net = MLP(in_features=3, out_features=21 ** 2, hidden_features=512, hidden_layers=8)
+    net.apply(initialize_weights)                                       # PSFNet.init_net applies it once more
+    got = np.asarray([[v.double().sum().item(), v.double().abs().sum().item()] for v in net.state_dict().values()])
+    np.testing.assert_allclose(got, g["mlp_checksum"], rtol=1e-12, atol=1e-12)
+
+
+def test_shard_bounds():
+    from sdirt_b200.sharding import shard_bounds, shard_slice
+    for n in (0, 1, 7, 4096, 131072):
+        for w in (1, 2, 3, 8):
+            b = shard_bounds(n, w)
+            assert b[0] == 0 and b[-1] == n and len(b) == w + 1
+            sizes = np.diff(b)
+            assert sizes.max() - sizes.min() <= 1 and (sizes >= 0).all()
+    assert shard_slice(10, 1, 4) == slice(3, 6)
+
+
+def _gather_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from sdirt_b200.sharding import gather_blocks, shard_slice
+    n_total = 7                                                    # ragged: 4 + 3
+    full = torch.arange(n_total * 2 * 3 * 3, dtype=torch.float32).reshape(n_total, 2, 3, 3)
+    sl = shard_slice(n_total)
+    out = gather_blocks(full[sl].clone(), n_total)
+    ret[rank] = bool(torch.equal(out, full)) and (sl == (slice(0, 4) if rank == 0 else slice(4, 7)))
+    dist.destroy_process_group()
+
+
+def test_gather_blocks_gloo_world2():
+    world, port = 2, 29500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gather_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
+
+
+def test_bench_workload_shape():
+    sys.path.insert(0, ROOT)
+    import bench
+    p = bench.bank_points(0)
+    assert p.shape == (4096, 3) and abs(float(p[0, 0]) + 127 / 128) < 1e-6 and abs(float(p[0, 1]) - 127 / 128) < 1e-6
+    depths = [float(bench.bank_points(s)[0, 2]) for s in range(32)]
+    assert min(depths) >= -20000 - 1e-3 and max(depths) <= -200 + 1e-3 and len(set(depths)) == 32

@@ -25,9 +25,12 @@ def main():
     pup = torch.stack([rr * torch.cos(th), rr * torch.sin(th)], -1).to(dev)
     cpup = (pup[:2048] * 0.25).contiguous()
     centre = E.psf_centre(h, 0.589, pts, cpup, pz)
-    for mode in ("per_ray", [10, 3, 4, 3, 4, 0, 3, 3, 4, 5, 3, 3] if name == "rf50mm" else None):
-        if mode is None:
+    want = os.environ.get("QB_MODES", "strict,replay,hybrid,fast").split(",")
+    for mode, numerics in (("per_ray", "strict"), ([10, 3, 4, 3, 4, 0, 3, 3, 4, 5, 3, 3] if name == "rf50mm" else None, "strict"), ("per_ray", "hybrid"), ("per_ray", "fast")):
+        if mode is None or (numerics if mode == "per_ray" else "replay") not in want:
             continue
+        import functools
+        E.psf_bank = functools.partial(E.psf_bank.func if hasattr(E.psf_bank, "func") else E.psf_bank, numerics=numerics)
         for _ in range(2):
             L, R, cnt = E.psf_bank(h, 0.589, pts, pup, pz, centre, 21, 0.046875, newton=mode, want_counts=True)
         torch.cuda.synchronize()
@@ -38,7 +41,7 @@ def main():
             L, R, cnt = E.psf_bank(h, 0.589, pts, pup, pz, centre, 21, 0.046875, newton=mode, want_counts=True)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print(f"{name} N={npts} spp={spp} newton={'per_ray' if mode == 'per_ray' else 'replay'}: {ms:.2f} ms  "
+        print(f"{name} N={npts} spp={spp} newton={'per_ray' if mode == 'per_ray' else 'replay'} {numerics}: {ms:.2f} ms  "
               f"{npts * spp / ms * 1e3:.3e} rays/s  valid frac {cnt.float().mean().item() / spp:.3f}")
     # fp32 FMA probe
     blocks, threads, iters = 148 * 8, 256, 1 << 16
