@@ -120,15 +120,16 @@ def test_ray_reaction_single_surface(golden, lenses):
     lens = lenses["rf50mm"]
     r0 = g["rf50mm_w589_ray0"]
     ray = Ray(torch.from_numpy(r0[..., :3].copy()), torch.from_numpy(r0[..., 3:6].copy()), wvln=0.589, device=DEV)
-    assert np.array_equal(ray.d.cpu().numpy(), r0[..., 3:6])               # re-normalising unit vectors is a no-op here
+    assert np.abs(ray.d.cpu().numpy() - r0[..., 3:6]).max() < 1.5e-7        # Ray() re-normalises, like the reference
     st = g["rf50mm_w589_states"]
     for i, s in enumerate(lens.surfaces):
         ray = s.ray_reaction(ray)
         assert np.array_equal(ray.ra.cpu().numpy(), st[i][..., 6])
-        assert np.abs(ray.o.cpu().numpy() - st[i][..., :3]).max() < 2e-4
+        # Ray() re-normalised d (1 ulp), which the 2..20 m lever arm to the first surface turns into <= 3e-3 mm
+        assert np.abs(ray.o.cpu().numpy() - st[i][..., :3]).max() < 3e-3
         assert np.abs(ray.d.cpu().numpy() - st[i][..., 3:6]).max() < 3e-6
     ray = ray.propagate_to(lens.d_sensor)
-    assert np.abs(ray.o.cpu().numpy() - g["rf50mm_w589_sensor"][..., :3]).max() < 1e-4
+    assert np.abs(ray.o.cpu().numpy() - g["rf50mm_w589_sensor"][..., :3]).max() < 1e-3
 
 
 def test_render_api_vs_reference(golden):
