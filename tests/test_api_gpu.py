@@ -127,7 +127,8 @@ def test_ray_reaction_single_surface(golden, lenses):
         assert np.array_equal(ray.ra.cpu().numpy(), st[i][..., 6])
         # Ray() re-normalised d (1 ulp), which the 2..20 m lever arm to the first surface turns into <= 3e-3 mm
         assert np.abs(ray.o.cpu().numpy() - st[i][..., :3]).max() < 3e-3
-        assert np.abs(ray.d.cpu().numpy() - st[i][..., 3:6]).max() < 3e-6
+        # ... and, through the surface normal at the shifted hit (curvature up to 0.04 /mm), into <= 1e-4 of direction
+        assert np.abs(ray.d.cpu().numpy() - st[i][..., 3:6]).max() < 1e-4
     ray = ray.propagate_to(lens.d_sensor)
     assert np.abs(ray.o.cpu().numpy() - g["rf50mm_w589_sensor"][..., :3]).max() < 1e-3
 
