@@ -164,6 +164,17 @@ int sdirt_psf_bank(const sdirt_lens *lens, double wvln_um,
                    float *out_l_dev, float *out_r_dev, int64_t *valid_count_dev,
                    void *workspace_dev, int64_t workspace_bytes, void *stream);
 
+/* ---- spatial ordering of the shared pupil samples (setup of the fused kernel's run-length splat) -----
+ * The PSF of a point is a SUM over the pupil samples of sample_from_points (optics.py:483-490), so their order is
+ * free.  sdirt_psf_bank gives each thread a contiguous run of samples and accumulates the bilinear taps of
+ * consecutive rays in registers while they fall on the same sensor pixel; samples sorted along a Morton curve
+ * over the pupil disc (|x|,|y| <= radius) make those runs compact patches of the pupil and hence of the PSF.
+ * sorted_out[n,2] receives the permuted samples (must not alias pupil_xy).  Unsorted input to sdirt_psf_bank is
+ * still correct, only slower. */
+int64_t sdirt_pupil_sort_workspace(int64_t n_samples);
+int sdirt_pupil_sort(const float *pupil_xy_dev, int64_t n_samples, double radius, float *sorted_out_dev,
+                     void *workspace_dev, int64_t workspace_bytes, void *stream);
+
 /* ---- splat of already-traced rays (forward_integral) ----------------------------------------------
  * o[spp,N,3], d[spp,N,3], ra[spp,N] as the reference's Ray holds them (sample-major).  centre_dev may
  * be NULL: the ra-weighted centroid of each point's hits is used (monte_carlo.py:28-31).  Raw sums. */

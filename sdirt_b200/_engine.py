@@ -62,6 +62,9 @@ def lib():
     L.sdirt_psf_bank_workspace.restype = i64
     L.sdirt_psf_bank.argtypes = [vp, dbl, vp, i64, vp, i64, dbl, vp, cint, dbl, C.POINTER(DPParams), C.POINTER(Options),
                                  cint, vp, vp, vp, vp, i64, vp]
+    L.sdirt_pupil_sort_workspace.argtypes = [i64]
+    L.sdirt_pupil_sort_workspace.restype = i64
+    L.sdirt_pupil_sort.argtypes = [vp, i64, dbl, vp, vp, i64, vp]
     L.sdirt_splat_rays.argtypes = [vp, vp, vp, i64, i64, vp, cint, dbl, C.POINTER(DPParams), vp, vp, vp, i64, vp]
     L.sdirt_render_local_psf.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
     L.sdirt_fp32_peak_probe.argtypes = [vp, cint, cint, cint, vp]
@@ -216,6 +219,20 @@ def _workspace(device, nbytes):
         ws = torch.empty(int(nbytes), device=device, dtype=torch.uint8)
         _ws_cache[key] = ws
     return ws
+
+
+def pupil_sort(pupil_xy, radius):
+    """Morton-ordered copy of the shared pupil samples [m, 2] (the order of a PSF's ray sum is free; the fused kernel's
+    run-length splat is fastest when consecutive samples are neighbours in the pupil)."""
+    m = pupil_xy.shape[0]
+    out = torch.empty_like(pupil_xy)
+    if m == 0:
+        return out
+    nbytes = lib().sdirt_pupil_sort_workspace(m)
+    ws = torch.empty(int(nbytes), device=pupil_xy.device, dtype=torch.uint8)
+    _check(lib().sdirt_pupil_sort(_dev(pupil_xy, "pupil_xy"), m, float(radius), _dev(out, "sorted"), C.c_void_p(ws.data_ptr()),
+                                  ws.numel(), _stream(pupil_xy)))
+    return out
 
 
 def psf_bank(lens, wvln, points, pupil_xy, pupil_z, centre, ks, pixel_size, dp=None, newton=None, normalise=1,

@@ -128,13 +128,17 @@ class Lensgroup(DeepObj):
     # ==============================================================================================
     # Sampling (optics.py:460-494, 816-858)
     # ==============================================================================================
-    def _pupil_samples(self, spp, shrink_pupil=False):
-        """Shared pupil disc samples, CPU generator, theta first then rho^2 (optics.py:482-487)."""
+    def _pupil_samples(self, spp, shrink_pupil=False, spatial_order=False):
+        """Shared pupil disc samples, CPU generator, theta first then rho^2 (optics.py:482-487).  `spatial_order`
+        returns the same set Morton-sorted on the device (a PSF is a sum over the set, so its order is free)."""
         pupilz, pupilr = self.entrance_pupil(shrink_pupil=shrink_pupil)
         theta = torch.rand(spp) * 2 * np.pi
         r = torch.sqrt(torch.rand(spp) * pupilr ** 2)
         xy = torch.stack((r * torch.cos(theta), r * torch.sin(theta)), 1)
-        return xy.to(self.device).contiguous(), pupilz
+        xy = xy.to(self.device, non_blocking=True).contiguous()
+        if spatial_order:
+            xy = E.pupil_sort(xy, pupilr)
+        return xy, pupilz
 
     @torch.no_grad()
     def sample_from_points(self, o=[[0, 0, -10000]], spp=256, wvln=DEFAULT_WAVE, shrink_pupil=False, normalized=False):
@@ -259,7 +263,7 @@ class Lensgroup(DeepObj):
             points = points.unsqueeze(0)
         point_obj = self._object_points(points)
         pts = point_obj.to(self.device).contiguous()
-        xy, pupilz = self._pupil_samples(spp)                              # main bundle first ...
+        xy, pupilz = self._pupil_samples(spp, spatial_order=self.numerics in ("fast", "hybrid"))   # main bundle first ...
         if center:
             centre = self.psf_center(point_obj)                          # ... then the chief-ray bundle (RNG order)
         else:

@@ -130,7 +130,7 @@ def test_ray_reaction_single_surface(golden, lenses):
         # ... and, through the surface normal at the shifted hit (curvature up to 0.04 /mm), into <= 1e-4 of direction
         assert np.abs(ray.d.cpu().numpy() - st[i][..., 3:6]).max() < 1e-4
     ray = ray.propagate_to(lens.d_sensor)
-    assert np.abs(ray.o.cpu().numpy() - g["rf50mm_w589_sensor"][..., :3]).max() < 1e-3
+    assert np.abs(ray.o.cpu().numpy() - g["rf50mm_w589_sensor"][..., :3]).max() < 3e-3
 
 
 def test_render_api_vs_reference(golden):

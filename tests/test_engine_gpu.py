@@ -315,3 +315,70 @@ def test_render_local_psf(golden, ks, half):
     np.testing.assert_allclose(rr.cpu().numpy(), g[f"ks{ks}_rr"], rtol=1.1e-3, atol=1e-6)
     ol, orr = O.render_local_psf(g[f"ks{ks}_img"], g[f"ks{ks}_psf"].astype(np.float32), ks)
     assert (rl.cpu().numpy() == ol).mean() > 0.95
+
+
+def _bank_inputs(name, n_pts=12, spp=60000, seed=11):
+    lens = make_lens(name, {"rf50mm": 0.40959781408309937, "rf35mm": 0.5514792203903198}[name])
+    pz, pr = {"rf50mm": (22.51324462890625, 6.019352912902832), "rf35mm": (14.338210105895996, 4.767455577850342)}[name]
+    rng = np.random.default_rng(seed)
+    ds = D_SENSOR[name]
+    ptsn = np.concatenate([rng.uniform(-1, 1, (n_pts, 2)), -rng.uniform(250, 20000, (n_pts, 1)) + ds], -1).astype(np.float32)
+    ptsn[0] = [0, 0, -1000 + ds]                       # in focus: every ray on the same 2x2 taps
+    ptsn[1] = [0.98, -0.98, -20000 + ds]               # field corner, far: strongest vignetting
+    obj = O.object_points(lens, ptsn)
+    px, py = torch_pupil(rng.uniform(0, 1, (2, spp)).astype(np.float32), pr)
+    cray = O.rays_from_points(obj, *torch_pupil(rng.uniform(0, 1, (2, 512)).astype(np.float32), pr / 4), pz)
+    O.trace_to_sensor(lens, cray, newton_iters="per_ray")
+    return lens, obj, np.stack([px, py], -1), pz, pr, O.chief_ray_centre(cray)
+
+
+@pytest.mark.parametrize("name", ["rf50mm", "rf35mm"])
+def test_pupil_sort_is_a_permutation_and_order_free(name):
+    """sdirt_pupil_sort returns the same sample set (Morton order); PSFs from sorted and unsorted samples agree to
+    summation-order noise; the specialised kernels agree with the strict arithmetic to the 1e-4 PSF criterion."""
+    from sdirt_b200 import _engine as E
+    lens, obj, pup, pz, pr, centre = _bank_inputs(name)
+    h = engine_lens(name)
+    pup_d = cu(pup)
+    srt = E.pupil_sort(pup_d, pr)
+    a = np.sort(pup_d.cpu().numpy().view(np.complex64).ravel())
+    b = np.sort(srt.cpu().numpy().view(np.complex64).ravel())
+    assert np.array_equal(a, b)
+    assert not np.array_equal(pup_d.cpu().numpy(), srt.cpu().numpy())
+    # neighbours along the sorted sequence are neighbours in the pupil
+    step = np.hypot(*np.diff(srt.cpu().numpy(), axis=0).T)
+    assert np.median(step) < 0.02 * pr
+    Ls, Rs, cs = E.psf_bank(h, 0.589, cu(obj), cu(pup), pz, cu(centre), 21, lens.pixel_size, numerics="strict", normalise=0,
+                            want_counts=True)
+    for numerics in ("fast", "hybrid"):
+        Lu, Ru, cu_ = E.psf_bank(h, 0.589, cu(obj), pup_d, pz, cu(centre), 21, lens.pixel_size, numerics=numerics, normalise=0,
+                                 want_counts=True)
+        Lq, Rq, cq = E.psf_bank(h, 0.589, cu(obj), srt, pz, cu(centre), 21, lens.pixel_size, numerics=numerics, normalise=0,
+                                want_counts=True)
+        assert torch.equal(cu_, cq)
+        assert l1_sumnorm(Lu.cpu().numpy(), Lq.cpu().numpy()).max() < 2e-6
+        assert l1_sumnorm(Ru.cpu().numpy(), Rq.cpu().numpy()).max() < 2e-6
+        # 60 k rays: a float32-level shift of a ray across a pixel-pair boundary is 1/60000 of a PSF's weight
+        assert l1_sumnorm(Lq.cpu().numpy(), Ls.cpu().numpy()).max() < 3e-4
+        assert l1_sumnorm(Rq.cpu().numpy(), Rs.cpu().numpy()).max() < 3e-4
+        assert (cq - cs).abs().max().item() <= 3
+        # total weight: a ray that moves across the window edge changes it by its own d_l (< 0.6)
+        np.testing.assert_allclose(Lq.sum((1, 2)).cpu().numpy(), Ls.sum((1, 2)).cpu().numpy(), rtol=2e-5, atol=2.0)
+
+
+def test_generic_loop_fallback_matches_specialised():
+    """A lens whose structure has no compiled specialisation (rf50mm with its last element removed) runs the same
+    fused kernel around the generic surface loop; on rf50mm itself both routes exist and must agree."""
+    from sdirt_b200 import _engine as E
+    from sdirt_b200.prescription import load_lens_json
+    lens, obj, pup, pz, pr, centre = _bank_inputs("rf50mm", n_pts=6, spp=30000)
+    recs, _, _ = load_lens_json(lens_path("rf50mm"))
+    cut = E.LensHandle(recs[:10], 62.25)                                  # 10 surfaces: no signature matches
+    srt = E.pupil_sort(cu(pup), pr)
+    Ls, Rs = E.psf_bank(cut, 0.589, cu(obj), srt, pz, cu(centre) * 0, 41, 0.2, numerics="strict", normalise=0)
+    for numerics in ("fast", "hybrid"):
+        Lf, Rf = E.psf_bank(cut, 0.589, cu(obj), srt, pz, cu(centre) * 0, 41, 0.2, numerics=numerics, normalise=0)
+        assert float(Ls.sum()) > 1000
+        assert l1_sumnorm(Lf.cpu().numpy()[:1], Ls.cpu().numpy()[:1]).max() < 3e-4
+        np.testing.assert_allclose(Lf.sum((1, 2)).cpu().numpy(), Ls.sum((1, 2)).cpu().numpy(), rtol=1e-4, atol=1e-3)
+        np.testing.assert_allclose(Rf.sum((1, 2)).cpu().numpy(), Rs.sum((1, 2)).cpu().numpy(), rtol=1e-4, atol=1e-3)

@@ -24,12 +24,15 @@ def main():
     rr = torch.sqrt(torch.rand(spp, generator=g) * pr ** 2)
     pup = torch.stack([rr * torch.cos(th), rr * torch.sin(th)], -1).to(dev)
     cpup = (pup[:2048] * 0.25).contiguous()
+    pup_sorted = E.pupil_sort(pup, pr)
+    pup_raw = pup
     centre = E.psf_centre(h, 0.589, pts, cpup, pz)
     want = os.environ.get("QB_MODES", "strict,replay,hybrid,fast").split(",")
     for mode, numerics in (("per_ray", "strict"), ([10, 3, 4, 3, 4, 0, 3, 3, 4, 5, 3, 3] if name == "rf50mm" else None, "strict"), ("per_ray", "hybrid"), ("per_ray", "fast")):
         if mode is None or (numerics if mode == "per_ray" else "replay") not in want:
             continue
         import functools
+        pup = pup_raw if numerics == 'strict' else pup_sorted
         E.psf_bank = functools.partial(E.psf_bank.func if hasattr(E.psf_bank, "func") else E.psf_bank, numerics=numerics)
         for _ in range(2):
             L, R, cnt = E.psf_bank(h, 0.589, pts, pup, pz, centre, 21, 0.046875, newton=mode, want_counts=True)
