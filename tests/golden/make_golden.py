@@ -214,6 +214,44 @@ def golden_psf2m():
     np.savez_compressed(os.path.join(HERE, "psf2m.npz"), **out)
 
 
+def golden_psf2m_sweep():
+    """2 M rays per point along the depth axis (0.5 ... 20 m) at the field corner and at mid field: how the float32
+    lattice of the reference's first-surface hit (ulp of |o| ~ 1e2 ... 8e3 mm) shows up in its PSFs with distance."""
+    out = {}
+    spp = 2_000_000
+    lens = make_lens("rf50mm")
+    ds = lens.d_sensor
+    dist = [500, 1000, 2000, 4000, 8000, 20000]
+    pts = [[0.98, -0.98, -d + ds] for d in dist] + [[-0.5, 0.45, -d + ds] for d in (1500, 3000, 6000, 12000)]
+    pts = torch.tensor(pts, dtype=torch.float32)
+    out["points_norm"] = pts.numpy()
+    out["hfov"] = np.float64(lens.hfov)
+    pz, pr = lens.entrance_pupil()
+    out["pupil"] = np.asarray([pz, pr], np.float64)
+    for tag in ("l", "r"):
+        torch.manual_seed(21)
+        u = [torch.rand(spp).numpy() for _ in range(2)]
+        torch.manual_seed(21)
+        out[tag] = np.concatenate([lens.psf_diff(pts[i:i + 5], ks=21, spp=spp, param_list=DP + (tag,)).numpy()
+                                   if i == 0 else _psf_same_seed(lens, pts[i:i + 5], spp, tag) for i in range(0, len(pts), 5)])
+        out["u_check"] = np.asarray([float(v.astype(np.float64).sum()) for v in u] + [spp])
+    depth = pts[:, 2]
+    scale = lens.calc_scale_pinhole(depth)
+    obj = pts.clone()
+    obj[:, 0] = pts[:, 0] * scale * lens.sensor_size[1] / 2
+    obj[:, 1] = pts[:, 1] * scale * lens.sensor_size[0] / 2
+    out["points_obj"] = obj.numpy()
+    torch.manual_seed(21)
+    torch.rand(spp), torch.rand(spp)
+    out["centre"] = lens.psf_center(obj).numpy()
+    np.savez_compressed(os.path.join(HERE, "psf2m_sweep.npz"), **out)
+
+
+def _psf_same_seed(lens, pts, spp, tag):
+    torch.manual_seed(21)
+    return lens.psf_diff(pts, ks=21, spp=spp, param_list=DP + (tag,)).numpy()
+
+
 def golden_render():
     torch.manual_seed(11)
     lens = make_lens("rf50mm", res=(32, 48))
