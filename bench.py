@@ -308,7 +308,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sdirt_b200", choices=["sdirt_b200", "reference"])
-    ap.add_argument("--numerics", default="hybrid", choices=["strict", "hybrid", "fast"])
+    ap.add_argument("--numerics", default="adaptive", choices=["strict", "hybrid", "adaptive", "fast"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -22,7 +22,7 @@ class Options(C.Structure):
 
 
 NEWTON_REPLAY, NEWTON_PER_RAY = 0, 1
-NUMERICS_STRICT, NUMERICS_FAST, NUMERICS_HYBRID = 0, 1, 2
+NUMERICS_STRICT, NUMERICS_FAST, NUMERICS_HYBRID, NUMERICS_ADAPTIVE = 0, 1, 2, 3
 DEFAULT_NUMERICS = NUMERICS_STRICT
 
 
@@ -128,8 +128,10 @@ def make_options(newton=None, numerics=None):
         n.numerics = NUMERICS_FAST
     elif numerics in ("hybrid", NUMERICS_HYBRID):
         n.numerics = NUMERICS_HYBRID
+    elif numerics in ("adaptive", NUMERICS_ADAPTIVE):
+        n.numerics = NUMERICS_ADAPTIVE
     else:
-        raise ValueError(f"numerics must be 'strict', 'hybrid' or 'fast', got {numerics!r}")
+        raise ValueError(f"numerics must be 'strict', 'hybrid', 'adaptive' or 'fast', got {numerics!r}")
     return n
 
 

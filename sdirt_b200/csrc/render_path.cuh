@@ -1,0 +1,431 @@
+// render_path.cuh — spatially varying dual-pixel render (local_psf_render_fast, deeplens/render_psf.py:120-155),
+// the HBM-streaming kernel.  Included by engine.cu.
+//
+// out_c(p) = sum over the ks x ks window of  pad_c(p + (u,v)) * psf_side(p)[ks-1-u, ks-1-v]   for side = L, R,
+// with the reference's half() arithmetic: image and kernels rounded to fp16, every product rounded to fp16, the sum
+// accumulated wider and rounded to fp16 once.  The per-pixel kernels [B,H,W,2,ks,ks] ARE the traffic (1764 B per pixel
+// at ks = 21 in fp16 against 36 B of image in and out), so the kernel is a pure stream over that tensor:
+//
+//   * one warp per output pixel; lanes own fixed *aligned pairs of taps* of the pixel's contiguous 2*ks*ks block, so a
+//     warp reads the block with 4-byte (fp16) / 8-byte (fp32) coalesced loads and no per-tap index arithmetic: every
+//     lane precomputes its (at most 14 + 2) tap positions once per CTA;
+//   * the replicate-padded image tile lives in shared memory as fp16, column-mirrored (so that increasing tap index
+//     is increasing address) and in two copies shifted by one element (so that the two image values a tap pair needs
+//     are ONE aligned 32-bit word whatever the pixel's column parity);
+//   * products are HMUL2 (two fp16-rounded products per instruction), accumulated with sm_100's mixed-precision
+//     add (PTX add.rn.f32.f16 -> SASS FHADD: f32 += f16 half of a register) -- the reference's rounding, 1.5
+//     instructions per multiply-accumulate;
+//   * degamma (psfnet.py:589-603) is applied while the tile is staged, gamma + clip (psfnet.py:605-620, 711-713) when
+//     the pixel is written.
+#pragma once
+
+#define RP_TH 16
+#define RP_TW 32
+#define RP_WARPS 8
+#define RP_C 3
+
+__device__ __forceinline__ void fhadd(float &acc, __half h) {
+    asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(acc) : "h"(__half_as_ushort(h)));
+}
+
+// Sum six per-lane partials over the warp with 8 shuffles instead of 30: at each of the first three butterfly levels a
+// lane keeps one value of a pair and ships the other, so the number of live values halves as the lane count does.
+// Returns the total of value `index` (0..5 = side * 3 + channel) on the lanes listed by reduce6_writer().
+__device__ __forceinline__ float reduce6(const float (&acc)[2][RP_C], int lane, int &index) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float k0 = b4 ? acc[0][1] : acc[0][0], s0 = b4 ? acc[0][0] : acc[0][1];
+    float k1 = b4 ? acc[1][0] : acc[0][2], s1 = b4 ? acc[0][2] : acc[1][0];
+    float k2 = b4 ? acc[1][2] : acc[1][1], s2 = b4 ? acc[1][1] : acc[1][2];
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    k2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+    float c0 = b3 ? k1 : k0, t0 = b3 ? k0 : k1;
+    c0 += __shfl_xor_sync(0xffffffffu, t0, 8);
+    k2 += __shfl_xor_sync(0xffffffffu, k2, 8);
+    float d = b2 ? k2 : c0, t1 = b2 ? c0 : k2;
+    d += __shfl_xor_sync(0xffffffffu, t1, 4);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    index = b2 ? 4 + (b4 ? 1 : 0) : (b3 ? 2 : 0) + (b4 ? 1 : 0);
+    return d;
+}
+__device__ __forceinline__ bool reduce6_writer(int lane) { return (lane & 3) == 0 && lane != 12 && lane != 28; }
+
+template <typename PsfT> struct PsfPair;
+template <> struct PsfPair<__half> {
+    static __device__ __forceinline__ __half2 load2(const __half *p) { return *reinterpret_cast<const __half2 *>(p); }
+    static __device__ __forceinline__ __half load1(const __half *p) { return *p; }
+};
+template <> struct PsfPair<float> {
+    static __device__ __forceinline__ __half2 load2(const float *p) {
+        const float2 v = *reinterpret_cast<const float2 *>(p);
+        return __floats2half2_rn(v.x, v.y);
+    }
+    static __device__ __forceinline__ __half load1(const float *p) { return __float2half_rn(*p); }
+};
+
+template <int KS, int TWPX = RP_TW>
+struct RenderGeom {
+    static constexpr int PR = (KS - 1) / 2;            // aligned tap pairs per kernel row
+    static constexpr int NP = 2 * KS * PR;             // pair units per pixel (both sides)
+    static constexpr int NS = 2 * KS;                  // single taps per pixel (one per kernel row and side)
+    static constexpr int NIT = (NP + 31) / 32;         // pair iterations per lane
+    static constexpr int NSI = (NS + 31) / 32;         // single iterations per lane
+    static constexpr int TH = RP_TH + KS - 1, TW = TWPX + KS - 1;
+    static constexpr int RW = (TW + 2) / 2;            // 32-bit words per tile row (TW + 1 halves, rounded up)
+    static constexpr int CHW = TH * RW;                // words per channel
+    static constexpr int COPYW = RP_C * CHW;           // words per parity copy
+    static constexpr int SMEM_BYTES = 2 * COPYW * 4;
+    static_assert(2 * COPYW < 65536, "tile word offsets are packed into 16 bits");
+};
+
+template <int KS, typename PsfT>
+__global__ void __launch_bounds__(RP_WARPS * 32, 3)
+render_pairs_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf, int B, int H, int W, int tone,
+                    float *__restrict__ out_l, float *__restrict__ out_r) {
+    using G = RenderGeom<KS>;
+    extern __shared__ unsigned rp_smem[];               // [2 copies][C][TH][RW] words of two fp16 each
+    __half *s0h = reinterpret_cast<__half *>(rp_smem);  // copy 0 addressed by element
+    constexpr int pad = (KS - 1) / 2;
+    const int b = blockIdx.z, y0 = blockIdx.y * RP_TH, x0 = blockIdx.x * RP_TW;
+
+    // ---- stage the mirrored tile: copy 0 element (r, m) = image(y0 + r - pad, x0 + (TW-1-m) - pad), replicate-padded
+    for (int i = threadIdx.x; i < RP_C * G::TH * 2 * G::RW; i += blockDim.x) {
+        const int c = i / (G::TH * 2 * G::RW), rem = i - c * (G::TH * 2 * G::RW);
+        const int r = rem / (2 * G::RW), m = rem - r * (2 * G::RW);
+        float v = 0.0f;
+        if (m < G::TW) {
+            const int gy = min(max(y0 + r - pad, 0), H - 1), gx = min(max(x0 + (G::TW - 1 - m) - pad, 0), W - 1);
+            v = img[(((int64_t)b * RP_C + c) * H + gy) * W + gx];
+            if (tone & 1) v = tone_degamma(v);
+        }
+        s0h[i] = __float2half_rn(v);
+    }
+    __syncthreads();
+    // copy 1 word w of a row = elements (2w+1, 2w+2) of copy 0
+    for (int i = threadIdx.x; i < G::COPYW; i += blockDim.x) {
+        const int w = i % G::RW;
+        const __half lo = s0h[2 * i + 1];
+        const __half hi = (w + 1 < G::RW) ? s0h[2 * i + 2] : __float2half_rn(0.0f);
+        rp_smem[G::COPYW + i] = (unsigned)__half_as_ushort(lo) | ((unsigned)__half_as_ushort(hi) << 16);
+    }
+    __syncthreads();
+
+    // ---- per-lane tap tables (pixel independent) -------------------------------------------------------------------
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned peo[G::NIT];                               // smem word offsets: low 16 bits even pixel column, high 16 odd
+    int pg[G::NIT];                                     // global half2 index inside the pixel's block
+    unsigned side_mask = 0, live_mask = 0;
+#pragma unroll
+    for (int i = 0; i < G::NIT; ++i) {
+        const int q = lane + 32 * i;
+        const bool live = q < G::NP;
+        const int qq = live ? q : 0;
+        const int side = qq / (KS * G::PR), rem = qq - side * (KS * G::PR);
+        const int u = rem / G::PR, m = rem - u * G::PR;
+        const int v0 = 2 * m + ((side + u) & 1);
+        const int K = RP_TW - 1 + v0, A = (KS - 1 - u) * G::RW;
+        peo[i] = (unsigned)(A + (K >> 1) + (K & 1) * G::COPYW) | ((unsigned)(A + ((K - 1) >> 1) + ((K - 1) & 1) * G::COPYW) << 16);
+        pg[i] = (side * KS * KS + u * KS + v0) >> 1;
+        side_mask |= (unsigned)side << i;
+        live_mask |= (unsigned)live << i;
+    }
+    int sh[G::NSI], sg[G::NSI];                         // smem half offset (copy 0), global element index
+    unsigned sside = 0, slive = 0;
+#pragma unroll
+    for (int i = 0; i < G::NSI; ++i) {
+        const int s = lane + 32 * i;
+        const bool live = s < G::NS;
+        const int ss = live ? s : 0;
+        const int side = ss / KS, u = ss - side * KS;
+        const int v = ((side + u) & 1) ? 0 : KS - 1;
+        sh[i] = (KS - 1 - u) * 2 * G::RW + RP_TW - 1 + v;
+        sg[i] = side * KS * KS + u * KS + v;
+        sside |= (unsigned)side << i;
+        slive |= (unsigned)live << i;
+    }
+
+    // ---- pixels: warp w owns tile rows w, w + 8 -----------------------------------------------------------------------
+    for (int ly = warp; ly < RP_TH; ly += RP_WARPS) {
+        const int y = y0 + ly;
+        if (y >= H) break;
+        for (int lx = 0; lx < RP_TW; ++lx) {
+            const int x = x0 + lx;
+            if (x >= W) break;
+            const PsfT *kp = psf + (((int64_t)b * H + y) * W + x) * (2 * KS * KS);
+            const int base = ly * G::RW - (lx >> 1);
+            const bool odd = lx & 1;
+            float acc[2][RP_C];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) acc[s][c] = 0.0f;
+            __half2 kv[G::NIT];
+#pragma unroll
+            for (int i = 0; i < G::NIT; ++i)
+                kv[i] = ((live_mask >> i) & 1) ? PsfPair<PsfT>::load2(kp + 2 * pg[i]) : __float2half2_rn(0.0f);
+            __half ks1[G::NSI];
+#pragma unroll
+            for (int i = 0; i < G::NSI; ++i)
+                ks1[i] = ((slive >> i) & 1) ? PsfPair<PsfT>::load1(kp + sg[i]) : __float2half_rn(0.0f);
+#pragma unroll
+            for (int i = 0; i < G::NIT; ++i) {
+                const int w = base + (int)(odd ? (peo[i] >> 16) : (peo[i] & 0xffffu));
+                constexpr int half_units = KS * G::PR;
+                const bool all0 = 32 * i + 31 < half_units, all1 = 32 * i >= half_units;   // compile time after unrolling
+                const bool side = all1 ? true : (all0 ? false : (bool)((side_mask >> i) & 1));
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) {
+                    const unsigned word = rp_smem[w + c * G::CHW];
+                    const __half2 p = __hmul2(kv[i], *reinterpret_cast<const __half2 *>(&word));
+                    if (!side) { fhadd(acc[0][c], __low2half(p)); fhadd(acc[0][c], __high2half(p)); }
+                    else { fhadd(acc[1][c], __low2half(p)); fhadd(acc[1][c], __high2half(p)); }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < G::NSI; ++i) {
+                const int hidx = ly * 2 * G::RW + sh[i] - lx;
+                const bool side = (sside >> i) & 1;
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) {
+                    const __half p = __hmul(ks1[i], s0h[hidx + c * 2 * G::CHW]);
+                    if (side) fhadd(acc[1][c], p); else fhadd(acc[0][c], p);
+                }
+            }
+            int oi;
+            float v = reduce6(acc, lane, oi);
+            if (reduce6_writer(lane)) {
+                const int s = oi / RP_C, c = oi - s * RP_C;
+                v = __half2float(__float2half_rn(v));
+                if (tone & 2) v = fminf(fmaxf(tone_gamma(v), 0.0f), 1.0f);
+                (s ? out_r : out_l)[(((int64_t)b * RP_C + c) * H + y) * W + x] = v;
+            }
+        }
+    }
+}
+
+template <int KS>
+static int launch_render_pairs(const float *img, const void *psf, int psf_is_half, int B, int H, int W, int tone,
+                               float *out_l, float *out_r, cudaStream_t st) {
+    using G = RenderGeom<KS>;
+    dim3 grid((W + RP_TW - 1) / RP_TW, (H + RP_TH - 1) / RP_TH, B);
+    if (psf_is_half) {
+        CUDA_TRY(cudaFuncSetAttribute(render_pairs_kernel<KS, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+        render_pairs_kernel<KS, __half><<<grid, RP_WARPS * 32, G::SMEM_BYTES, st>>>(img, (const __half *)psf, B, H, W, tone, out_l, out_r);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(render_pairs_kernel<KS, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+        render_pairs_kernel<KS, float><<<grid, RP_WARPS * 32, G::SMEM_BYTES, st>>>(img, (const float *)psf, B, H, W, tone, out_l, out_r);
+    }
+    return check_launch("render_pairs_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same arithmetic with the kernels streamed by the TMA unit.
+//
+// The direct kernel above keeps one pixel's 1764 B in flight per warp (registers), ~42 KB per SM: about what
+// Little's law asks for at HBM3e latency, i.e. no slack -> 0.33 of the HBM roofline (r01f).  Here the per-pixel kernel
+// blocks of SEG consecutive pixels of a tile row -- one contiguous, 16-byte aligned run of the [B,H,W,2,ks,ks] tensor
+// -- are fetched by ONE cp.async.bulk (UBLKCP) into a 3-stage shared-memory ring guarded by mbarriers; two stages
+// (113 KB) are in flight while the 16 warps of the CTA consume the third.  Needs W % SEG == 0 (the host picks).
+// ------------------------------------------------------------------------------------------------
+#define RS_WARPS 16
+#define RS_STAGES 3
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int KS, typename PsfT, int SEG>
+struct StreamGeom {
+    using G = RenderGeom<KS, SEG>;
+    static constexpr int PIX_BYTES = 2 * KS * KS * (int)sizeof(PsfT);
+    static constexpr int STAGE_BYTES = SEG * PIX_BYTES;
+    static constexpr int TILE_OFF = RS_STAGES * STAGE_BYTES;                 // image tile after the ring
+    static constexpr int BAR_OFF = (TILE_OFF + G::SMEM_BYTES + 15) / 16 * 16;
+    static constexpr int SMEM_BYTES = BAR_OFF + 2 * RS_STAGES * 8;
+    static_assert(STAGE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+};
+
+template <int KS, typename PsfT, int SEG>
+__global__ void __launch_bounds__(RS_WARPS * 32, 1)
+render_stream_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf, int B, int H, int W, int tone,
+                     float *__restrict__ out_l, float *__restrict__ out_r) {
+    using SG = StreamGeom<KS, PsfT, SEG>;
+    using G = typename SG::G;
+    extern __shared__ __align__(128) unsigned char rs_raw[];
+    unsigned *tile = reinterpret_cast<unsigned *>(rs_raw + SG::TILE_OFF);
+    __half *s0h = reinterpret_cast<__half *>(tile);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(rs_raw + SG::BAR_OFF), *empty = full + RS_STAGES;
+    constexpr int pad = (KS - 1) / 2;
+    const int b = blockIdx.z, y0 = blockIdx.y * RP_TH, x0 = blockIdx.x * SEG;
+    const int nrows = min(RP_TH, H - y0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RS_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, RS_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int row) {
+        const int st = row % RS_STAGES;
+        mbar_expect_tx(full + st, SG::STAGE_BYTES);
+        bulk_g2s(rs_raw + st * SG::STAGE_BYTES, psf + (((int64_t)b * H + (y0 + row)) * W + x0) * (2 * KS * KS), SG::STAGE_BYTES, full + st);
+    };
+    if (threadIdx.x == 0)
+        for (int row = 0; row < min(RS_STAGES, nrows); ++row) issue(row);
+
+    // ---- image tile (mirrored, two parity copies), while the first rows are in flight ------------------------------------
+    for (int i = threadIdx.x; i < RP_C * G::TH * 2 * G::RW; i += blockDim.x) {
+        const int c = i / (G::TH * 2 * G::RW), rem = i - c * (G::TH * 2 * G::RW);
+        const int r = rem / (2 * G::RW), m = rem - r * (2 * G::RW);
+        float v = 0.0f;
+        if (m < G::TW) {
+            const int gy = min(max(y0 + r - pad, 0), H - 1), gx = min(max(x0 + (G::TW - 1 - m) - pad, 0), W - 1);
+            v = img[(((int64_t)b * RP_C + c) * H + gy) * W + gx];
+            if (tone & 1) v = tone_degamma(v);
+        }
+        s0h[i] = __float2half_rn(v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G::COPYW; i += blockDim.x) {
+        const int w = i % G::RW;
+        const __half lo = s0h[2 * i + 1];
+        const __half hi = (w + 1 < G::RW) ? s0h[2 * i + 2] : __float2half_rn(0.0f);
+        tile[G::COPYW + i] = (unsigned)__half_as_ushort(lo) | ((unsigned)__half_as_ushort(hi) << 16);
+    }
+    __syncthreads();
+
+    // ---- per-lane tap tables: byte offsets, for THIS warp's pixel-column parity (lx = warp, warp + 16, ...: fixed parity) ----
+    static_assert(RS_WARPS % 2 == 0, "a warp's pixel columns must share their parity");
+    const int par = warp & 1;
+    int ia[G::NIT], ga[G::NIT];                          // image word / kernel pair byte offsets
+    unsigned side_mask = 0;
+#pragma unroll
+    for (int i = 0; i < G::NIT; ++i) {
+        const int q = min(lane + 32 * i, G::NP - 1);    // lanes past the last unit repeat it with a zero kernel
+        const int side = q / (KS * G::PR), rem = q - side * (KS * G::PR);
+        const int u = rem / G::PR, m = rem - u * G::PR;
+        const int v0 = 2 * m + ((side + u) & 1);
+        const int K = SEG - 1 + v0 - par, A = (KS - 1 - u) * G::RW;
+        ia[i] = 4 * (A + (K >> 1) + (K & 1) * G::COPYW);
+        ga[i] = (side * KS * KS + u * KS + v0) * (int)sizeof(PsfT);
+        side_mask |= (unsigned)side << i;
+    }
+    int sh[G::NSI], sg[G::NSI];
+    unsigned sside = 0;
+#pragma unroll
+    for (int i = 0; i < G::NSI; ++i) {
+        const int ss = min(lane + 32 * i, G::NS - 1);
+        const int side = ss / KS, u = ss - side * KS;
+        const int v = ((side + u) & 1) ? 0 : KS - 1;
+        sh[i] = 2 * ((KS - 1 - u) * 2 * G::RW + SEG - 1 + v);
+        sg[i] = (side * KS * KS + u * KS + v) * (int)sizeof(PsfT);
+        sside |= (unsigned)side << i;
+    }
+    const unsigned char *tile_b = reinterpret_cast<const unsigned char *>(tile);
+
+    // ---- rows of the tile, one ring stage each; a warp takes pixels warp, warp + 16, ... of the row ----------------------
+    for (int ly = 0; ly < nrows; ++ly) {
+        const int st = ly % RS_STAGES;
+        const unsigned phase = (unsigned)(ly / RS_STAGES) & 1u;
+        mbar_wait(full + st, phase);
+        const PsfT *stage = reinterpret_cast<const PsfT *>(rs_raw + st * SG::STAGE_BYTES);
+        const int y = y0 + ly;
+        for (int lx = warp; lx < SEG; lx += RS_WARPS) {
+            const unsigned char *kb = rs_raw + st * SG::STAGE_BYTES + lx * SG::PIX_BYTES;
+            const unsigned char *pb = tile_b + 4 * (ly * G::RW - (lx >> 1));
+            float acc[2][RP_C];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) acc[s][c] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < G::NIT; ++i) {
+                constexpr int half_units = KS * G::PR;
+                const bool all_live = 32 * i + 31 < G::NP;                                   // compile time after unrolling
+                const bool all0 = 32 * i + 31 < half_units, all1 = 32 * i >= half_units;
+                __half2 kv = PsfPair<PsfT>::load2(reinterpret_cast<const PsfT *>(kb + ga[i]));
+                if (!all_live && lane + 32 * i >= G::NP) kv = __float2half2_rn(0.0f);
+                const unsigned char *wp = pb + ia[i];
+                const bool side = all1 ? true : (all0 ? false : (bool)((side_mask >> i) & 1));
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) {
+                    const unsigned word = *reinterpret_cast<const unsigned *>(wp + c * (4 * G::CHW));
+                    const __half2 p = __hmul2(kv, *reinterpret_cast<const __half2 *>(&word));
+                    if (!side) { fhadd(acc[0][c], __low2half(p)); fhadd(acc[0][c], __high2half(p)); }
+                    else { fhadd(acc[1][c], __low2half(p)); fhadd(acc[1][c], __high2half(p)); }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < G::NSI; ++i) {
+                const bool all_live = 32 * i + 31 < G::NS;
+                __half k1 = PsfPair<PsfT>::load1(reinterpret_cast<const PsfT *>(kb + sg[i]));
+                if (!all_live && lane + 32 * i >= G::NS) k1 = __float2half_rn(0.0f);
+                const unsigned char *hp = tile_b + 2 * (ly * 2 * G::RW - lx) + sh[i];
+                const bool side = (sside >> i) & 1;
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) {
+                    const __half p = __hmul(k1, *reinterpret_cast<const __half *>(hp + c * (4 * G::CHW)));
+                    if (side) fhadd(acc[1][c], p); else fhadd(acc[0][c], p);
+                }
+            }
+            int oi;
+            float v = reduce6(acc, lane, oi);
+            if (reduce6_writer(lane)) {
+                const int s = oi / RP_C, c = oi - s * RP_C;
+                v = __half2float(__float2half_rn(v));
+                if (tone & 2) v = fminf(fmaxf(tone_gamma(v), 0.0f), 1.0f);
+                (s ? out_r : out_l)[(((int64_t)b * RP_C + c) * H + y) * W + (x0 + lx)] = v;
+            }
+        }
+        // this warp is done with the stage; warp 0 refills it with row ly + STAGES once every warp has let go
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);
+        if (threadIdx.x == 0 && ly + RS_STAGES < nrows) {
+            mbar_wait(empty + st, phase);
+            issue(ly + RS_STAGES);
+        }
+    }
+}
+
+// W % SEG == 0 and 16-byte aligned rows are what the bulk copies need; anything else runs the direct kernel.
+template <int KS>
+static int launch_render(const float *img, const void *psf, int psf_is_half, int B, int H, int W, int tone,
+                         float *out_l, float *out_r, cudaStream_t st) {
+    if (psf_is_half && W % 32 == 0 && ((uintptr_t)psf & 15) == 0) {
+        using SG = StreamGeom<KS, __half, 32>;
+        if (SG::SMEM_BYTES <= 227 * 1024) {
+            dim3 grid(W / 32, (H + RP_TH - 1) / RP_TH, B);
+            CUDA_TRY(cudaFuncSetAttribute(render_stream_kernel<KS, __half, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG::SMEM_BYTES));
+            render_stream_kernel<KS, __half, 32><<<grid, RS_WARPS * 32, SG::SMEM_BYTES, st>>>(img, (const __half *)psf, B, H, W, tone, out_l, out_r);
+            return check_launch("render_stream_kernel");
+        }
+    }
+    if (!psf_is_half && W % 16 == 0 && ((uintptr_t)psf & 15) == 0) {
+        using SG = StreamGeom<KS, float, 16>;
+        if (SG::SMEM_BYTES <= 227 * 1024) {
+            dim3 grid(W / 16, (H + RP_TH - 1) / RP_TH, B);
+            CUDA_TRY(cudaFuncSetAttribute(render_stream_kernel<KS, float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG::SMEM_BYTES));
+            render_stream_kernel<KS, float, 16><<<grid, RS_WARPS * 32, SG::SMEM_BYTES, st>>>(img, (const float *)psf, B, H, W, tone, out_l, out_r);
+            return check_launch("render_stream_kernel");
+        }
+    }
+    return launch_render_pairs<KS>(img, psf, psf_is_half, B, H, W, tone, out_l, out_r, st);
+}

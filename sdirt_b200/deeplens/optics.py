@@ -263,7 +263,7 @@ class Lensgroup(DeepObj):
             points = points.unsqueeze(0)
         point_obj = self._object_points(points)
         pts = point_obj.to(self.device).contiguous()
-        xy, pupilz = self._pupil_samples(spp, spatial_order=self.numerics in ("fast", "hybrid"))   # main bundle first ...
+        xy, pupilz = self._pupil_samples(spp, spatial_order=self.numerics in ("fast", "hybrid", "adaptive"))   # main bundle first ...
         if center:
             centre = self.psf_center(point_obj)                          # ... then the chief-ray bundle (RNG order)
         else:

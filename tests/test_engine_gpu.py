@@ -382,3 +382,84 @@ def test_generic_loop_fallback_matches_specialised():
         assert l1_sumnorm(Lf.cpu().numpy()[:1], Ls.cpu().numpy()[:1]).max() < 3e-4
         np.testing.assert_allclose(Lf.sum((1, 2)).cpu().numpy(), Ls.sum((1, 2)).cpu().numpy(), rtol=1e-4, atol=1e-3)
         np.testing.assert_allclose(Rf.sum((1, 2)).cpu().numpy(), Rs.sum((1, 2)).cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("numerics", ["replay", "strict", "hybrid", "adaptive", "fast"])
+def test_psf_bank_2m_depth_sweep(golden, numerics):
+    """2 M rays per point from 0.5 m to 20 m at the field corner and at mid field, against the reference.
+
+    The float32 lattice of the reference's first hit (ulp of |o_x|, |o_y|) grows with distance: `fast` drifts from
+    1e-5 (<= 2 m) to 1.1e-4 (20 m field corner); strict / hybrid / adaptive reproduce the lattice (<= 2e-5), `replay`
+    (strict with the reference's own bundle-global Newton loop counts, recorded with the golden) is at 3e-6.  The one
+    exception is the field corner exactly in focus (1 m), 1.0 ... 1.2e-4 for EVERY mode including the bit-exact replay:
+    there the whole PSF is four taps, and the reference adds 2 M weights of ~0.4 one after the other into a float32
+    sum of ~5e5 (index_put_ accumulate, monte_carlo.py:225-235), which alone is wrong by several 1e-4 relative
+    (np.cumsum in float32 reproduces that); the engine sums per-thread runs, then chunks, and is the more exact side."""
+    from sdirt_b200 import _engine as E
+    g = golden("psf2m_sweep")
+    lens = make_lens("rf50mm", g["hfov"])
+    chk = g["u_check"]
+    spp = int(chk[2])
+    torch.manual_seed(21)
+    u = [torch.rand(spp).numpy(), torch.rand(spp).numpy()]
+    np.testing.assert_allclose([float(v.astype(np.float64).sum()) for v in u], chk[:2], rtol=0, atol=0)
+    pz, pr = g["pupil"]
+    px, py = torch_pupil(np.stack(u), pr)
+    h = engine_lens("rf50mm")
+    pup = cu(np.stack([px, py], -1))
+    pts, ctr = cu(g["points_obj"]), cu(g["centre"])
+    if numerics == "replay":
+        # the reference traced the points in two bundles of five; each bundle has its own global loop counts
+        outs = [E.psf_bank(h, 0.589, pts[i:i + 5].contiguous(), pup, float(pz), ctr[i:i + 5].contiguous(), 21, lens.pixel_size,
+                           numerics="strict", newton=[int(c) for c in g["newton_counts"][i // 5]]) for i in (0, 5)]
+        L, R = torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+    else:
+        if numerics != "strict":
+            pup = E.pupil_sort(pup, float(pr))
+        L, R = E.psf_bank(h, 0.589, pts, pup, float(pz), ctr, 21, lens.pixel_size, numerics=numerics)
+    l1l, l1r = l1_sumnorm(L.cpu().numpy(), g["l"]), l1_sumnorm(R.cpu().numpy(), g["r"])
+    print(numerics, "depth sweep, distance mm:", (-(g["points_norm"][:, 2] - 62.25)).round())
+    print(numerics, "2M-ray L1 (L):", np.array2string(l1l, precision=2, max_line_width=200), "(R):",
+          np.array2string(l1r, precision=2, max_line_width=200))
+    in_focus_corner = 1
+    others = np.arange(len(l1l)) != in_focus_corner
+    assert max(l1l[in_focus_corner], l1r[in_focus_corner]) < 1.3e-4
+    if numerics == "replay":
+        assert max(l1l[others].max(), l1r[others].max()) < 1.5e-5
+    elif numerics == "fast":
+        assert max(l1l.max(), l1r.max()) < 1.5e-4
+        assert max(l1l[[0, 2, 3, 6, 7, 8]].max(), l1r[[0, 2, 3, 6, 7, 8]].max()) < 3e-5   # <= 6 m: no visible lattice yet
+    else:
+        assert max(l1l[others].max(), l1r[others].max()) < (3e-5 if numerics == "adaptive" else 2e-5)
+
+
+@pytest.mark.parametrize("ks", [7, 11, 21])
+@pytest.mark.parametrize("half", [False, True])
+def test_render_streamed_kernel_vs_oracle(ks, half):
+    """Widths that are multiples of the row-segment size take the TMA-streamed render kernel (mbarrier ring of bulk
+    copies); heights that are not multiples of the tile exercise its partial tiles.  Same fp16 arithmetic as the
+    direct kernel: against the oracle's restatement of local_psf_render_fast, and against the direct kernel."""
+    from sdirt_b200 import _engine as E
+    rng = np.random.default_rng(ks)
+    B, H, W = 2, 40, 96
+    img = rng.uniform(0, 1, (B, 3, H, W)).astype(np.float32)
+    psf = rng.uniform(0, 1, (B, H, W, 2, ks, ks)).astype(np.float32) ** 4
+    psf = (psf / psf.sum((-1, -2), keepdims=True)).astype(np.float16)
+    ol, orr = O.render_local_psf(img, psf.astype(np.float32), ks)
+    pt = torch.from_numpy(psf).to(DEV)
+    pt = pt if half else pt.float()
+    rl, rr = E.render_local_psf(cu(img), pt.contiguous(), ks)
+    for got, want in ((rl, ol), (rr, orr)):
+        got = got.cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=1.1e-3, atol=1e-6)
+        assert (got == want).mean() > 0.95
+    # the direct kernel on a crop whose width is not a multiple of the segment: identical pixels away from the crop edge
+    wc = W - 10
+    rl2, rr2 = E.render_local_psf(cu(img[..., :wc]), pt[:, :, :wc].contiguous(), ks)
+    inner = slice(0, wc - ks)
+    assert torch.equal(rl2[..., inner], rl[..., inner]) and torch.equal(rr2[..., inner], rr[..., inner])
+    # tone curves fused on both routes
+    tl, tr = E.render_local_psf(cu(img), pt.contiguous(), ks, tone=3)
+    tl2, tr2 = E.render_local_psf(cu(img[..., :wc]), pt[:, :, :wc].contiguous(), ks, tone=3)
+    assert torch.equal(tl2[..., inner], tl[..., inner]) and torch.equal(tr2[..., inner], tr[..., inner])
+    assert float(tl.min()) >= 0.0 and float(tl.max()) <= 1.0

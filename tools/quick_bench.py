@@ -27,8 +27,8 @@ def main():
     pup_sorted = E.pupil_sort(pup, pr)
     pup_raw = pup
     centre = E.psf_centre(h, 0.589, pts, cpup, pz)
-    want = os.environ.get("QB_MODES", "strict,replay,hybrid,fast").split(",")
-    for mode, numerics in (("per_ray", "strict"), ([10, 3, 4, 3, 4, 0, 3, 3, 4, 5, 3, 3] if name == "rf50mm" else None, "strict"), ("per_ray", "hybrid"), ("per_ray", "fast")):
+    want = os.environ.get("QB_MODES", "strict,replay,hybrid,adaptive,fast").split(",")
+    for mode, numerics in (("per_ray", "strict"), ([10, 3, 4, 3, 4, 0, 3, 3, 4, 5, 3, 3] if name == "rf50mm" else None, "strict"), ("per_ray", "hybrid"), ("per_ray", "adaptive"), ("per_ray", "fast")):
         if mode is None or (numerics if mode == "per_ray" else "replay") not in want:
             continue
         import functools
