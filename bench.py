@@ -170,7 +170,13 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the JSON line must be the only thing on stdout: NCCL_DEBUG=VERSION (set in some images) prints a banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
+        # torchrun pins OMP_NUM_THREADS=1; the host side of the end-to-end path (the reference's CPU RNG + polar transform of
+        # the shared sample set, optics.py:483-487) may use this rank's share of the cores
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
 
     def barrier():
         if world > 1:
@@ -271,12 +277,53 @@ def run_gpu(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = None
+    try:                                   # dram__bytes_read + write of one psf_bank_run_kernel launch of THIS workload (ncu)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "bank_kernel_traffic.json")))["bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": None,
-                "note": "psf_bank_kernel is FP32-issue bound, not HBM/tensor bound; peak = FFMA micro-benchmark measured in "
-                        "this run (MEASURED_PEAKS.json has no fp32 entry; its hbm_gbs=%s). achieved = %.0f flop/ray "
-                        "(SURVEY 8d) x rays/s of the kernel alone. HBM traffic per launch is ~30 MB (ncu, profiles/)."
+                "traffic": traffic, "kernel": "psf_bank_run_kernel<TraceSig<Sig_rf50mm, ...>>",
+                "note": "the dominant kernel (99.7 %% of a step, profiles/) is FP32-issue bound, not HBM/tensor bound: it reads "
+                        "12 B/point + the L2-resident 16 MB sample set and writes 7 KB/point. peak = FFMA micro-benchmark "
+                        "measured in this run (MEASURED_PEAKS.json has no fp32 entry; its hbm_gbs=%s). achieved = %.0f "
+                        "flop/ray (SURVEY 8d: the reference algorithm's minimal per-ray count) x rays per launch / CUDA-event "
+                        "time of the step's launches (dp_lut + bank + finalize); traffic = ncu dram bytes per launch."
                         % (peaks.get("hbm_gbs"), FLOP_PER_RAY)}
+
+    # ---- secondary numbers (not the contract metric): other numerics modes, and the HBM-bound render kernel --------------
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    modes = {}
+    sub = slabs[args.warmup][::16].contiguous()                      # 256 points of the first timed slab
+    subc = centres[args.warmup][::16].contiguous()
+    torch.manual_seed(1234)
+    raw = torch.stack((rho * torch.cos(theta), rho * torch.sin(theta)), 1).to(dev).contiguous()
+    for mode in ("strict", "hybrid", "adaptive", "fast"):
+        pup = raw if mode == "strict" else pupil
+        ms = timed(lambda: E.psf_bank(handle, 0.589, sub, pup, pz, subc, KS, lens.pixel_size, numerics=mode), 2)
+        modes[mode] = sub.shape[0] * SPP / (ms * 1e-3)
+    rb, rh, rw = 2, 1024, 1536
+    g = torch.Generator(device=dev).manual_seed(0)
+    img = torch.rand((rb, 3, rh, rw), device=dev, generator=g)
+    psf = torch.rand((rb, rh, rw, 2, KS, KS), device=dev, generator=g, dtype=torch.float16)
+    ms = timed(lambda: E.render_local_psf(img, psf, KS, tone=3), 5)
+    rbytes = rb * rh * rw * (2 * KS * KS * 2 + 3 * 4 + 6 * 4)
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    render = {"metric": "pixels/s, spatially varying DP render (explicit fp16 per-pixel PSFs, degamma+gamma fused)",
+              "value": rb * rh * rw / (ms * 1e-3), "unit": "pixels/s", "shape": [rb, 3, rh, rw], "ks": KS,
+              "roofline": {"bound": "hbm", "achieved": rbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": rbytes / (ms * 1e-3) / 1e9 / hbm, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    del psf, img
 
     # ---- CPU baseline on this box's host cores (bounded sample) --------------------------------------
     cpu = None
@@ -297,6 +344,8 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "numerics_modes_rays_per_s": modes,
+        "render": render,
     }))
     if world > 1:
         dist.destroy_process_group()

@@ -171,3 +171,24 @@ def test_tone_fused_matches_reference_curves(golden):
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_psfnet_fitting_loop(tmp_path, lenses):
+    """The PSF-bank workload generators and a few steps of PSFNet.train_psfnet (psfnet.py:101-241): ray-traced targets from
+    the engine, MLP step in torch, no host round trip of the PSFs."""
+    lens = lenses["rf50mm"]
+    torch.manual_seed(0)
+    np.random.seed(0)
+    inp, psf = lens.get_training_data(bs=16, spp=4000)
+    assert inp.shape == (16, 3) and psf.shape == (16, 21, 21) and psf.is_cuda
+    assert float(psf.amax((1, 2)).min()) > 0.99 and torch.isfinite(psf).all()       # every point produced a max-normalised PSF
+    assert float(inp[:, 2].min()) >= 0.0 and float(inp[:, 2].max()) <= 1.0
+    tin, tpsf = lens.get_test_data(bs=1024, spp=512)
+    assert tin.shape == (1024, 3) and tpsf.shape == (1024, 21, 21)
+    lens.numerics = "adaptive"
+    try:
+        hist = lens.train_psfnet(iters=4, bs=16, spp=2000, evaluate_every=4, result_dir=str(tmp_path))
+    finally:
+        lens.numerics = None
+    assert len(hist) == 5 and all(np.isfinite(hist))
+    assert (tmp_path / "iter4_PSFNet_mlp.pkl").exists()

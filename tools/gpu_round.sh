@@ -13,6 +13,8 @@ echo "== bench" ; timeout 1200 python bench.py --steps 3 --warmup 3 > $OUT/bench
 echo "== bench reference arm" ; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cat $OUT/bench_ref.json
 echo "== ncu launch list of the bench command"
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/bench_under_ncu.log 2>&1; echo "ncu launches exit $?"
+echo "== dram traffic of the bank kernel at the bench workload"
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:psf_bank_run -s 1 -c 1 --csv --log-file $OUT/bank_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/bank_traffic.log 2>&1; echo "ncu traffic exit $?"
 echo "== ncu full on the fused bank kernel"
 QB_MODES=adaptive timeout 1200 ncu --set full --clock-control none --import-source on -k regex:psf_bank -s 1 -c 1 -o $OUT/prof_bank -f python tools/quick_bench.py rf50mm 592 262144 > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?"
 QB_MODES=fast timeout 1200 ncu --set full --clock-control none --import-source on -k regex:psf_bank -s 1 -c 1 -o $OUT/prof_bank_fast -f python tools/quick_bench.py rf50mm 592 262144 > $OUT/ncu_full_fast.log 2>&1; echo "ncu full (fast) exit $?"
