@@ -405,10 +405,219 @@ render_stream_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lane-per-pixel streamed kernel (fp16 kernels, the tensor PSFNet.pred produces under CUDA autocast).
+//
+// The kernels above give every pixel to a warp (lanes over taps): each lane needs its own table of tap positions,
+// the six partial sums are warp-reduced per pixel, and the 10-pairs-then-a-single rhythm of a kernel row makes most
+// shared-memory loads 2-way bank conflicted (measured: 0.44 of the HBM roofline, shared-memory pipe bound).  Here the
+// 32 lanes of a warp ARE the 32 pixels of the staged row segment and a warp owns a few whole kernel rows of one side:
+//   * the per-pixel kernel blocks are KS*KS words apart in the stage (an odd stride): the 32 lanes of a load hit 32
+//     different banks; the image words of 32 neighbouring pixels are 16 consecutive words in each of two parity
+//     copies placed half a bank-cycle apart: conflict free as well (a third copy serves the odd-phase rows);
+//   * all lanes walk the same taps, so every address is lane base + immediate: no tables, no integer arithmetic;
+//   * every lane keeps its own pixel's sums: no shuffles; the 2*KS/TPW warps of a side add their partial sums
+//     through shared memory once per row.
+// Per multiply-accumulate: 1/2 LDS (kernel pair) + 3/2 LDS (image, 3 channels) + 3/2 HMUL2 + 3 FHADD per pair of taps.
+// ------------------------------------------------------------------------------------------------
+template <int KS>
+struct LaneGeom {
+    static constexpr int SEG = 32;
+    static constexpr int TPW = (KS % 3 == 0) ? 3 : 1;          // kernel rows (tasks) per warp, all of one side
+    static constexpr int NW = 2 * KS / TPW;                     // compute warps
+    static constexpr int TH = RP_TH + KS - 1, TW = SEG + KS - 1;
+    static constexpr int RW = (TW + 2) / 2;                     // words per tile row
+    static constexpr int CHW = TH * RW;                         // words per channel
+    static constexpr int COPY_RAW = RP_C * CHW;
+    // copy 1a starts at a word address == 16 (mod 32) after copy 0, copy 1b at == 17 (mod 32)
+    static constexpr int COPY1A = COPY_RAW + ((16 - COPY_RAW % 32) + 32) % 32;
+    static constexpr int COPY1B = COPY1A + COPY_RAW + ((17 - (COPY1A + COPY_RAW) % 32) + 32) % 32;
+    static constexpr int TILE_WORDS = COPY1B + COPY_RAW;
+    static constexpr int PIX_BYTES = 2 * KS * KS * 2;
+    static constexpr int STAGE_BYTES = SEG * PIX_BYTES;
+    static constexpr int TILE_OFF = RS_STAGES * STAGE_BYTES;
+    static constexpr int PART_OFF = (TILE_OFF + TILE_WORDS * 4 + 15) / 16 * 16;
+    static constexpr int PART_BYTES = 4 * NW * RP_C * 32 * 4;   // RL_PBUF buffers of [NW][C][32] floats
+    static constexpr int BAR_OFF = PART_OFF + PART_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + (2 * RS_STAGES + 2 * 4) * 8;
+    static_assert(STAGE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static_assert(KS % TPW == 0 && NW <= 30, "a warp's kernel rows must belong to one side; two more warps stream and reduce");
+};
+
+// One kernel row (21 taps at KS = 21) of one side for this lane's pixel.  P0 = parity of the row's first element in the
+// pixel's block: P0 = 0 -> aligned pairs at v = 0, 2, ..., single tap v = KS-1;  P0 = 1 -> single tap v = 0, pairs at 1, 3, ...
+//   kb: this lane's kernel block + byte offset of the row's first element
+//   ib: this lane's image word address for the row's first aligned pair (copy already chosen by lane parity)
+//   sb: address of the image element (copy 0) under the row's single tap
+template <int KS, int P0, int CHB>
+__device__ __forceinline__ void lane_row(const unsigned char *kb, const unsigned char *ib, const unsigned char *sb, float (&acc)[RP_C]) {
+    constexpr int PR = (KS - 1) / 2;
+#pragma unroll
+    for (int k = 0; k < PR; ++k) {
+        const __half2 kv = *reinterpret_cast<const __half2 *>(kb + 2 * P0 + 4 * k);
+#pragma unroll
+        for (int c = 0; c < RP_C; ++c) {
+            const __half2 p = __hmul2(kv, *reinterpret_cast<const __half2 *>(ib + 4 * k + c * CHB));
+            fhadd(acc[c], __low2half(p));
+            fhadd(acc[c], __high2half(p));
+        }
+    }
+    const __half k1 = *reinterpret_cast<const __half *>(kb + (P0 ? 0 : 2 * (KS - 1)));
+#pragma unroll
+    for (int c = 0; c < RP_C; ++c) fhadd(acc[c], __hmul(k1, *reinterpret_cast<const __half *>(sb + c * CHB)));
+}
+
+#define RL_PBUF 4     // partial-sum buffers between the compute warps and the reducer warp
+
+// Warp roles: warps 0 .. NW-1 compute (each a few kernel rows of one side, lanes = the 32 pixels of the row segment);
+// warps NW, NW+1 reduce one side each (add its NW/2 partial sums, round, tone-map, write the pixels); lane 0 of the first
+// also issues the bulk copies.  Everything between the roles is an mbarrier: compute warps never meet a CTA-wide barrier in the row loop.
+template <int KS>
+__global__ void __launch_bounds__((LaneGeom<KS>::NW + 2) * 32, 1)
+render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ psf, int B, int H, int W, int tone,
+                    float *__restrict__ out_l, float *__restrict__ out_r) {
+    using G = LaneGeom<KS>;
+    extern __shared__ __align__(128) unsigned char rl_raw[];
+    unsigned *tile = reinterpret_cast<unsigned *>(rl_raw + G::TILE_OFF);
+    __half *s0h = reinterpret_cast<__half *>(tile);
+    float *part = reinterpret_cast<float *>(rl_raw + G::PART_OFF);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(rl_raw + G::BAR_OFF), *empty = full + RS_STAGES;
+    unsigned long long *pfull = empty + RS_STAGES, *pempty = pfull + RL_PBUF;
+    constexpr int pad = (KS - 1) / 2, SEG = G::SEG, CHB = 4 * G::CHW;
+    const int b = blockIdx.z, y0 = blockIdx.y * RP_TH, x0 = blockIdx.x * SEG;
+    const int nrows = min(RP_TH, H - y0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RS_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, G::NW); }
+        for (int s = 0; s < RL_PBUF; ++s) { mbar_init(pfull + s, G::NW); mbar_init(pempty + s, 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int row) {
+        const int st = row % RS_STAGES;
+        mbar_expect_tx(full + st, G::STAGE_BYTES);
+        bulk_g2s(rl_raw + st * G::STAGE_BYTES, psf + (((int64_t)b * H + (y0 + row)) * W + x0) * (2 * KS * KS), G::STAGE_BYTES, full + st);
+    };
+    if (warp == G::NW && lane == 0)
+        for (int row = 0; row < min(RS_STAGES, nrows); ++row) issue(row);
+
+    // ---- image tile, column-mirrored: copy 0 (elements 2w, 2w+1 per word) and two instances of copy 1 (2w+1, 2w+2) ----
+    // loads first, eight at a time, so that a thread waits for HBM once per batch and not once per element
+    constexpr int TILE_ELEMS = RP_C * G::TH * 2 * G::RW;
+    for (int i0 = threadIdx.x; i0 < TILE_ELEMS; i0 += 8 * blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k * blockDim.x;
+            v[k] = 0.0f;
+            if (i < TILE_ELEMS) {
+                const int c = i / (G::TH * 2 * G::RW), rem = i - c * (G::TH * 2 * G::RW);
+                const int r = rem / (2 * G::RW), m = rem - r * (2 * G::RW);
+                if (m < G::TW) {
+                    const int gy = min(max(y0 + r - pad, 0), H - 1), gx = min(max(x0 + (G::TW - 1 - m) - pad, 0), W - 1);
+                    v[k] = __ldg(img + (((int64_t)b * RP_C + c) * H + gy) * W + gx);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k * blockDim.x;
+            if (i < TILE_ELEMS) {
+                const int m = i % (2 * G::RW);
+                s0h[i] = __float2half_rn((tone & 1) && m < G::TW ? tone_degamma(v[k]) : v[k]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G::COPY_RAW; i += blockDim.x) {
+        const int w = i % G::RW;
+        const __half lo = s0h[2 * i + 1];
+        const __half hi = (w + 1 < G::RW) ? s0h[2 * i + 2] : __float2half_rn(0.0f);
+        const unsigned word = (unsigned)__half_as_ushort(lo) | ((unsigned)__half_as_ushort(hi) << 16);
+        tile[G::COPY1A + i] = word;
+        tile[G::COPY1B + i] = word;
+    }
+    __syncthreads();
+
+    if (warp >= G::NW) {
+        // ---- reducer warps (one per side; the first also streams) ------------------------------------------------------------
+        const int s = warp - G::NW;
+        for (int ly = 0; ly < nrows; ++ly) {
+            const int st = ly % RS_STAGES, pb = ly % RL_PBUF;
+            if (s == 0 && lane == 0 && ly + RS_STAGES < nrows) {  // the stage of row ly is free once every compute warp let go
+                mbar_wait(empty + st, (unsigned)(ly / RS_STAGES) & 1u);
+                issue(ly + RS_STAGES);
+            }
+            __syncwarp();
+            mbar_wait(pfull + pb, (unsigned)(ly / RL_PBUF) & 1u);
+            const float *pr = part + pb * (G::NW * RP_C * 32);
+#pragma unroll
+            for (int c = 0; c < RP_C; ++c) {
+                const float *ps = pr + (s * (G::NW / 2)) * (RP_C * 32) + c * 32 + lane;
+                float v = 0.0f;
+#pragma unroll
+                for (int k = 0; k < G::NW / 2; ++k) v += ps[k * (RP_C * 32)];
+                v = __half2float(__float2half_rn(v));
+                if (tone & 2) v = fminf(fmaxf(tone_gamma(v), 0.0f), 1.0f);
+                (s ? out_r : out_l)[(((int64_t)b * RP_C + c) * H + (y0 + ly)) * W + (x0 + lane)] = v;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pempty + pb);
+        }
+        return;
+    }
+
+    // ---- compute warps: this warp's kernel rows and this lane's pixel ---------------------------------------------------------
+    // pixel lx = lane; tap (u, v) multiplies mirrored tile element (row ly + KS-1-u, m = SEG-1-lane + v)
+    const int side = warp / (G::NW / 2), u0 = (warp - side * (G::NW / 2)) * G::TPW;
+    const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
+    // first aligned pair of a P0 = 0 row: v = 0, m0 = 31 - lane: odd lanes -> copy 0 word (31-lane)/2, even lanes -> copy 1a word (30-lane)/2
+    const int img0 = (lane & 1) ? 4 * ((SEG - 1 - lane) >> 1) : 4 * (G::COPY1A + ((SEG - 2 - lane) >> 1));
+    // first aligned pair of a P0 = 1 row: v = 1, m0 = 32 - lane: even lanes -> copy 0 word (32-lane)/2, odd lanes -> copy 1b word (31-lane)/2
+    const int img1 = (lane & 1) ? 4 * (G::COPY1B + ((SEG - 1 - lane) >> 1)) : 4 * ((SEG - lane) >> 1);
+    const int sgl0 = 2 * (SEG - 1 - lane + KS - 1), sgl1 = 2 * (SEG - 1 - lane);      // single taps: v = KS-1 (P0 = 0), v = 0 (P0 = 1)
+
+    for (int ly = 0; ly < nrows; ++ly) {
+        const int st = ly % RS_STAGES, pb = ly % RL_PBUF;
+        mbar_wait(full + st, (unsigned)(ly / RS_STAGES) & 1u);
+        const unsigned char *kblock = rl_raw + st * G::STAGE_BYTES + lane * G::PIX_BYTES + 2 * side * KS * KS;
+        float acc[RP_C];
+#pragma unroll
+        for (int c = 0; c < RP_C; ++c) acc[c] = 0.0f;
+#pragma unroll
+        for (int t = 0; t < G::TPW; ++t) {
+            const int u = u0 + t;
+            const unsigned char *kb = kblock + 2 * u * KS;
+            const unsigned char *rowb = tb + 4 * ((ly + KS - 1 - u) * G::RW);
+            if ((side + u) & 1) lane_row<KS, 1, CHB>(kb, rowb + img1, rowb + sgl1, acc);
+            else lane_row<KS, 0, CHB>(kb, rowb + img0, rowb + sgl0, acc);
+        }
+        if (ly >= RL_PBUF) mbar_wait(pempty + pb, (unsigned)(ly / RL_PBUF - 1) & 1u);   // the reducer is done with this buffer
+        float *pw = part + (pb * G::NW + warp) * (RP_C * 32);
+#pragma unroll
+        for (int c = 0; c < RP_C; ++c) pw[c * 32 + lane] = acc[c];
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(empty + st); mbar_arrive(pfull + pb); }
+    }
+}
+
+template <int KS>
+static int launch_render_lanes(const float *img, const __half *psf, int B, int H, int W, int tone, float *out_l, float *out_r,
+                               cudaStream_t st) {
+    using G = LaneGeom<KS>;
+    dim3 grid(W / G::SEG, (H + RP_TH - 1) / RP_TH, B);
+    CUDA_TRY(cudaFuncSetAttribute(render_lanes_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+    render_lanes_kernel<KS><<<grid, (G::NW + 2) * 32, G::SMEM_BYTES, st>>>(img, psf, B, H, W, tone, out_l, out_r);
+    return check_launch("render_lanes_kernel");
+}
+
 // W % SEG == 0 and 16-byte aligned rows are what the bulk copies need; anything else runs the direct kernel.
 template <int KS>
 static int launch_render(const float *img, const void *psf, int psf_is_half, int B, int H, int W, int tone,
                          float *out_l, float *out_r, cudaStream_t st) {
+    if (psf_is_half && W % 32 == 0 && ((uintptr_t)psf & 15) == 0 && LaneGeom<KS>::SMEM_BYTES <= 227 * 1024)
+        return launch_render_lanes<KS>(img, (const __half *)psf, B, H, W, tone, out_l, out_r, st);
     if (psf_is_half && W % 32 == 0 && ((uintptr_t)psf & 15) == 0) {
         using SG = StreamGeom<KS, __half, 32>;
         if (SG::SMEM_BYTES <= 227 * 1024) {
@@ -429,3 +638,4 @@ static int launch_render(const float *img, const void *psf, int psf_is_half, int
     }
     return launch_render_pairs<KS>(img, psf, psf_is_half, B, H, W, tone, out_l, out_r, st);
 }
+

@@ -342,7 +342,18 @@ class Lensgroup(DeepObj):
 
     @torch.no_grad()
     def calc_entrance_pupil_paraxial(self, entrance=True):
-        """Pupil (z, radius) from 16 paraxial rays off the stop edge (optics.py:1335-1376)."""
+        """Pupil (z, radius) from 16 paraxial rays off the stop edge (optics.py:1335-1376).  The reference repeats this
+        trace inside every sample_from_points call; it depends on the prescription only, so the result is kept until a
+        surface changes (same value, one trace instead of two per psf() call)."""
+        key = (bool(entrance), self.aper_idx, tuple(s._state_key() for s in self.surfaces), str(self.device))
+        cache = self.__dict__.setdefault("_pupil_cache", {})
+        if key not in cache:
+            if len(cache) > 16:
+                cache.clear()
+            cache[key] = self._calc_entrance_pupil_paraxial(entrance)
+        return cache[key]
+
+    def _calc_entrance_pupil_paraxial(self, entrance=True):
         aper_z = self.surfaces[self.aper_idx].d.item()
         aper_r = self.surfaces[self.aper_idx].r
         delta_r = 1e-3
