@@ -27,12 +27,14 @@ sys.path.insert(0, ROOT)
 
 GRID, DEPTHS, SPP, KS = 64, 32, 2_000_000, 21
 SENSOR_RES = (512, 768)
-LENS = "rf50mm"
-FLOP_PER_RAY = 2.1e3     # algorithmic flop/ray, rf50mm, per-ray Newton counts (FMA = 2)
-# Derived once with the engine on a B200 (tests/test_api_gpu.py pins them against the reference's values):
-HFOV = {"rf50mm": 0.40959781408309937}
-PUPIL = {"rf50mm": (22.51324462890625, 6.019352912902832)}
-D_SENSOR = {"rf50mm": 62.25}
+LENS = "rf50mm"          # --lens rf35mm switches to BASELINE config 3's prescription (same bank shape)
+# algorithmic flop/ray with the reference's minimal per-ray Newton counts (FMA = 2)
+FLOPS_PER_RAY = {"rf50mm": 2.1e3, "rf35mm": 3.3e3}
+FLOP_PER_RAY = FLOPS_PER_RAY[LENS]
+# The reference's own setup values (tests/test_api_gpu.py pins the engine's against them):
+HFOV = {"rf50mm": 0.40959781408309937, "rf35mm": 0.5514792203903198}
+PUPIL = {"rf50mm": (22.51324462890625, 6.019352912902832), "rf35mm": (14.338210105895996, 4.767455577850342)}
+D_SENSOR = {"rf50mm": 62.25, "rf35mm": 80.447}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -279,11 +281,12 @@ def run_gpu(args):
         pass
     traffic = None
     try:                                   # dram__bytes_read + write of one psf_bank_run_kernel launch of THIS workload (ncu)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "bank_kernel_traffic.json")))["bytes_per_launch"]
+        if LENS == "rf50mm":
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "bank_kernel_traffic.json")))["bytes_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": traffic, "kernel": "psf_bank_run_kernel<TraceSig<Sig_rf50mm, ...>>",
+                "traffic": traffic, "kernel": "psf_bank_run_kernel<TraceSig<Sig_%s, ...>>" % LENS,
                 "note": "the dominant kernel (99.7 %% of a step, profiles/) is FP32-issue bound, not HBM/tensor bound: it reads "
                         "12 B/point + the L2-resident 16 MB sample set and writes 7 KB/point. peak = FFMA micro-benchmark "
                         "measured in this run (MEASURED_PEAKS.json has no fp32 entry; its hbm_gbs=%s). achieved = %.0f "
@@ -359,7 +362,10 @@ def main():
     ap.add_argument("--impl", default="sdirt_b200", choices=["sdirt_b200", "reference"])
     ap.add_argument("--numerics", default="adaptive", choices=["strict", "hybrid", "adaptive", "fast"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--lens", default="rf50mm", choices=sorted(HFOV), help="prescription (rf50mm = the headline config)")
     args = ap.parse_args()
+    global LENS, FLOP_PER_RAY
+    LENS, FLOP_PER_RAY = args.lens, FLOPS_PER_RAY[args.lens]
     if args.impl == "reference":
         run_reference(args)
     else:

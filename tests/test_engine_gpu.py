@@ -467,3 +467,59 @@ def test_render_streamed_kernel_vs_oracle(ks, half):
     tl2, tr2 = E.render_local_psf(cu(img[..., :wc]), pt[:, :, :wc].contiguous(), ks, tone=3)
     assert torch.allclose(tl2[..., inner], tl[..., inner], rtol=2e-3, atol=1e-5) and torch.allclose(tr2[..., inner], tr[..., inner], rtol=2e-3, atol=1e-5)
     assert float(tl.min()) >= 0.0 and float(tl.max()) <= 1.0
+
+
+@pytest.mark.parametrize("numerics", ["fast", "hybrid", "adaptive"])
+def test_fused_kernel_edge_shapes(numerics):
+    """The specialised fused kernel on ragged sample counts (1, 255, 4097: shorter than a thread run, not a multiple of
+    the CTA), a fully vignetted point, the smallest and the largest window, unsorted samples; against the strict kernel."""
+    from sdirt_b200 import _engine as E
+    name = "rf50mm"
+    lens = make_lens(name, 0.40959781408309937)
+    h = engine_lens(name)
+    rng = np.random.default_rng(5)
+    ptsn = np.concatenate([rng.uniform(-1, 1, (7, 2)), rng.uniform(-6000, -400, (7, 1))], -1).astype(np.float32)
+    obj = O.object_points(lens, ptsn)
+    obj[6] = [4000.0, 0.0, -500.0]                                   # far outside the field: no ray survives
+    cray = O.rays_from_points(obj, *torch_pupil(rng.uniform(0, 1, (2, 512)).astype(np.float32), 6.0193 / 4), 22.5132)
+    O.trace_to_sensor(lens, cray, newton_iters="per_ray")
+    centre = cu(O.chief_ray_centre(cray))
+    for spp, ks in ((1, 21), (255, 21), (4097, 21), (4097, 3), (4097, 63)):
+        u = rng.uniform(0, 1, (2, spp)).astype(np.float32)
+        pup = cu(np.stack(torch_pupil(u, 6.0193), -1))
+        Ls, Rs, cs = E.psf_bank(h, 0.589, cu(obj), pup, 22.5132, centre, ks, lens.pixel_size, normalise=0, want_counts=True,
+                                numerics="strict")
+        Lf, Rf, cf = E.psf_bank(h, 0.589, cu(obj), pup, 22.5132, centre, ks, lens.pixel_size, normalise=0, want_counts=True,
+                                numerics=numerics)
+        assert torch.isfinite(Lf).all() and torch.isfinite(Rf).all()
+        assert cf[6].item() == 0 and float(Lf[6].abs().sum()) == 0.0 and float(Rf[6].abs().sum()) == 0.0
+        assert (cf - cs).abs().max().item() <= 1                      # a ray on the window edge may fall either side
+        # total weight: equal up to the d_l (< 0.6) of such a ray and the 1e-5 of the d_l / d_r table
+        np.testing.assert_allclose(Lf.sum((1, 2)).cpu().numpy(), Ls.sum((1, 2)).cpu().numpy(), rtol=5e-5, atol=0.7)
+        np.testing.assert_allclose(Rf.sum((1, 2)).cpu().numpy(), Rs.sum((1, 2)).cpu().numpy(), rtol=5e-5, atol=0.7)
+        if spp >= 4097 and ks == 21:                                  # per-tap agreement once a tap holds many rays
+            assert np.abs(Lf.cpu().numpy() - Ls.cpu().numpy()).max() < 1.0
+    # max- and sum-normalised outputs of the fused kernel
+    Lm, Rm = E.psf_bank(h, 0.589, cu(obj[:6]), pup, 22.5132, centre[:6].contiguous(), 21, lens.pixel_size, normalise=1, numerics=numerics)
+    Lq, Rq = E.psf_bank(h, 0.589, cu(obj[:6]), pup, 22.5132, centre[:6].contiguous(), 21, lens.pixel_size, normalise=2, numerics=numerics)
+    assert abs(float(Lm.amax((1, 2)).min()) - 1.0) < 1e-5 and abs(float(Rm.amax((1, 2)).max()) - 1.0) < 1e-5
+    np.testing.assert_allclose(Lq.sum((1, 2)).cpu().numpy(), 1.0, rtol=1e-5)
+    np.testing.assert_allclose(Rq.sum((1, 2)).cpu().numpy(), 1.0, rtol=1e-5)
+
+
+def test_render_edge_shapes():
+    """Empty batch, one-pixel-high image, width below one tile, 4-channel fallback: no crash, same numbers as the oracle."""
+    from sdirt_b200 import _engine as E
+    rng = np.random.default_rng(3)
+    rl, rr = E.render_local_psf(torch.zeros((0, 3, 8, 8), device=DEV), torch.zeros((0, 8, 8, 2, 7, 7), device=DEV), 7)
+    assert rl.shape == (0, 3, 8, 8)
+    for (b, c, hh, ww, ks) in ((1, 3, 1, 5, 7), (1, 3, 3, 64, 11), (2, 1, 9, 33, 7), (1, 4, 6, 10, 5), (1, 3, 5, 32, 21)):
+        img = rng.uniform(0, 1, (b, c, hh, ww)).astype(np.float32)
+        psf = rng.uniform(0, 1, (b, hh, ww, 2, ks, ks)).astype(np.float32) ** 3
+        psf = (psf / psf.sum((-1, -2), keepdims=True)).astype(np.float16)
+        ol, orr = O.render_local_psf(img, psf.astype(np.float32), ks)
+        for half in (True, False):
+            pt = torch.from_numpy(psf).to(DEV)
+            rl, rr = E.render_local_psf(cu(img), (pt if half else pt.float()).contiguous(), ks)
+            np.testing.assert_allclose(rl.cpu().numpy(), ol, rtol=1.1e-3, atol=1e-6)
+            np.testing.assert_allclose(rr.cpu().numpy(), orr, rtol=1.1e-3, atol=1e-6)
