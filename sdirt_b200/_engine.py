@@ -267,7 +267,7 @@ def splat_rays(o, d, ra, centre, ks, pixel_size, dp=None):
     out_r = torch.empty((n, ks, ks), device=dev, dtype=torch.float32)
     if n > MAX_POINTS_PER_CALL:
         raise RuntimeError("sdirt_engine: split forward_integral calls above 65535 points")
-    nbytes = lib().sdirt_psf_bank_workspace(n, m, ks) + 8 * n
+    nbytes = lib().sdirt_psf_bank_workspace(n, m, ks) + 32 * n + 128
     ws = _workspace(dev, nbytes)
     dpp = make_dp(dp)
     _check(lib().sdirt_splat_rays(_dev(o, "o"), _dev(d, "d"), _dev(ra, "ra"), m, n,

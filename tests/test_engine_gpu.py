@@ -523,3 +523,22 @@ def test_render_edge_shapes():
             rl, rr = E.render_local_psf(cu(img), (pt if half else pt.float()).contiguous(), ks)
             np.testing.assert_allclose(rl.cpu().numpy(), ol, rtol=1.1e-3, atol=1e-6)
             np.testing.assert_allclose(rr.cpu().numpy(), orr, rtol=1.1e-3, atol=1e-6)
+
+
+def test_splat_rays_lanes_kernel_matches_point_kernel():
+    """forward_integral on a sample-major Ray with >= 32 points takes the lanes = points kernels (coalesced over the
+    [spp, N] layout); fewer points take the CTA-per-point kernels.  Same taps, same weights (table vs closed form)."""
+    from sdirt_b200 import _engine as E
+    lens, obj, pup, pz, pr, centre = _bank_inputs("rf50mm", n_pts=40, spp=3001, seed=7)
+    h = engine_lens("rf50mm")
+    o, d = E.sample_rays(cu(obj), cu(pup), pz)
+    ra = torch.ones(o.shape[:2], device=DEV)
+    E.trace_rays(h, 0.589, o.view(-1, 3), d.view(-1, 3), ra.view(-1), to_sensor=True, numerics="strict")
+    for ctr in (cu(centre), None):
+        L, R = E.splat_rays(o, d, ra, ctr, 21, lens.pixel_size)
+        parts = [E.splat_rays(o[:, a:b].contiguous(), d[:, a:b].contiguous(), ra[:, a:b].contiguous(),
+                              None if ctr is None else ctr[a:b].contiguous(), 21, lens.pixel_size) for a, b in ((0, 20), (20, 40))]
+        L2, R2 = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+        assert float(L2.sum()) > 1000
+        np.testing.assert_allclose(L.cpu().numpy(), L2.cpu().numpy(), rtol=3e-5, atol=3e-5)
+        np.testing.assert_allclose(R.cpu().numpy(), R2.cpu().numpy(), rtol=3e-5, atol=3e-5)
