@@ -21,8 +21,10 @@
  *                                      forward_integral                    deeplens/monte_carlo.py:9-68
  *                                      assign_points_to_pixels_small_r/big_r  deeplens/monte_carlo.py:135-372
  *   sdirt_splat_rays                <- forward_integral on an existing Ray deeplens/monte_carlo.py:9-68
- *   sdirt_render_local_psf          <- local_psf_render_fast               deeplens/render_psf.py:120-155
+ *   sdirt_render_local_psf(_rows)   <- local_psf_render_fast               deeplens/render_psf.py:120-155
  *                                      PSFNet.degamma / gamma / clip       deeplens/psfnet.py:589-620,706-713
+ *   sdirt_mlp_input_layer           <- coordinate grid + first Linear+ReLU deeplens/psfnet.py:681-694; psfnet_arch.py:40-41
+ *   sdirt_psf_pack                  <- PSFNet.pred: flip, stack, normalise deeplens/psfnet.py:326-333
  *
  * Conventions: every pointer marked "dev" is device memory owned by the caller (a torch CUDA tensor's
  * data_ptr); the library allocates nothing on the device.  All work is enqueued on `stream`
@@ -199,6 +201,29 @@ int sdirt_splat_rays(const float *o_dev, const float *d_dev, const float *ra_dev
 int sdirt_render_local_psf(const float *img_dev, const void *psf_dev, int psf_is_half,
                            int B, int C, int H, int W, int ks, int tone,
                            float *out_l_dev, float *out_r_dev, void *stream);
+
+/* The same for a window of rows [row0, row0 + n_rows) of every image: psf_rows_dev is [B, n_rows, W, 2, ks, ks] (the
+ * kernels of those rows only), img and the outputs are the whole [B,C,H,W] tensors (the window's halo rows are read
+ * from img, replicate padding applies at the IMAGE border only).  PSFNet.render walks an image in such bands so that
+ * the per-pixel PSF tensor (psfnet.py:705; 2.8 GB per 1024 x 1536 image in fp16) is only ever a band. */
+int sdirt_render_local_psf_rows(const float *img_dev, const void *psf_rows_dev, int psf_is_half,
+                                int B, int C, int H, int W, int row0, int n_rows, int ks, int tone,
+                                float *out_l_dev, float *out_r_dev, void *stream);
+
+/* ---- the two ends of PSFNet.pred inside PSFNet.render (psfnet.py:317-336, 681-705; psfnet_arch.py:40-41) ----------
+ * sdirt_mlp_input_layer: for the pixels of images [b0, b0 + nb), rows [row0, row0 + n_rows) build the MLP's first
+ * activation.  Pixel p = ((b - b0) * n_rows + (y - row0)) * W + x owns output rows 2p (left: input (xs[x], ys[y],
+ * z[b,y,x])) and 2p + 1 (right: (-xs[x], ys[y], z[b,y,x]), psfnet.py:328).  Row = relu(W1 . input + b1) with CUDA
+ * autocast's arithmetic: inputs / weights / bias in fp16, fp32 accumulation, one rounding to fp16.
+ *   xs[W], ys[H]: the linspace(-1,1,W) / linspace(1,-1,H) axes (psfnet.py:684-688); z[B,H,W]: depth2z(depth);
+ *   w1_half[n1,3], b1_half[n1]: the first Linear; out_half[2 * nb * n_rows * W, n1] fp16.
+ * sdirt_psf_pack: raw_half[2 * n_pixels, ld] fp16 = the last Linear + ReLU of those rows (ld >= ks*ks: the GEMM may
+ * pad its N) -> psf_half[n_pixels, 2, ks, ks] fp16 = stack(left, flip(right, -1)) / (sum(-1).sum(-1) + 1e-9) with
+ * torch's fp16 rounding points (psfnet.py:329-333).  All-zero kernels stay zero (the reference writes NaN there). */
+int sdirt_mlp_input_layer(const float *xs_dev, const float *ys_dev, const float *z_dev, int B, int H, int W,
+                          int b0, int nb, int row0, int n_rows, const void *w1_half_dev, const void *b1_half_dev,
+                          int n1, void *out_half_dev, void *stream);
+int sdirt_psf_pack(const void *raw_half_dev, int64_t n_pixels, int ld, int ks, void *psf_half_dev, void *stream);
 
 /* ---- measurement helper: dependent-free FP32 FMA loop, returns nothing; timed by the caller -------- */
 int sdirt_fp32_peak_probe(float *out_dev, int blocks, int threads, int iters, void *stream);

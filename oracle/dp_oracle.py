@@ -36,6 +36,7 @@ Reference sites restated (paths relative to /root/reference):
   deeplens/optics.py:1203-1233, 1335-1396, 1170-1196  calc_fov / entrance_pupil / refocus -> calc_hfov, pupil_paraxial, refocus
   deeplens/render_psf.py:120-155  local_psf_render_fast                     -> render_local_psf
   deeplens/psfnet.py:589-620      degamma / gamma                           -> degamma, gamma
+  deeplens/psfnet.py:317-336, 681-713; psfnet_arch.py:32-56  pred / render under CUDA autocast -> mlp_*_half, psf_pack_half, psfnet_render_half
 """
 from __future__ import annotations
 
@@ -790,3 +791,71 @@ def render_local_psf(img, psf, ks):
                 out[s] += (patch * k).astype(np.float16).astype(np.float32)
     out16 = out.astype(np.float16)
     return out16[0].astype(F32), out16[1].astype(F32)
+
+
+# ------------------------------------------------------------------------------------------------
+# PSFNet.pred / PSFNet.render under CUDA autocast (fp16 MLP), restated
+# ------------------------------------------------------------------------------------------------
+def _h(a):
+    """Round to fp16 and come back to float32 (one fp16 rounding point)."""
+    return np.asarray(a, dtype=F32).astype(np.float16).astype(F32)
+
+
+def mlp_linear_relu_half(x16, w, b):
+    """One Linear + ReLU of the PSF MLP under torch.autocast (psfnet_arch.py:40-56): activations, weights and bias in
+    fp16, products accumulated in float32 (float64 here: the fp32 sum of fp16 products is order dependent in the last
+    bit only), bias added before the single rounding to fp16, then ReLU."""
+    acc = _h(x16).astype(np.float64) @ _h(w).astype(np.float64).T + _h(b).astype(np.float64)
+    return np.maximum(_h(acc.astype(F32)), F32(0))
+
+
+def mlp_input_rows(xs, ys, z, b0, nb, row0, n_rows):
+    """MLP input rows for a window of pixels, pixel-major / side-minor: row 2p = (x, y, z), row 2p + 1 = (-x, y, z)
+    (psfnet.py:683-694, 328).  xs [W], ys [H], z [B,H,W] float32 -> [2P, 3] float32."""
+    zz = _f(z)[b0:b0 + nb, row0:row0 + n_rows]                              # [nb, n_rows, W]
+    x = np.broadcast_to(_f(xs)[None, None, :], zz.shape)
+    y = np.broadcast_to(_f(ys)[None, row0:row0 + n_rows, None], zz.shape)
+    left = np.stack((x, y, zz), -1).reshape(-1, 3)
+    right = left.copy()
+    right[:, 0] = -right[:, 0]
+    return np.stack((left, right), 1).reshape(-1, 3)
+
+
+def mlp_forward_half(weights, inp):
+    """The whole MLP (list of (W, b) pairs) on rows `inp` [M, 3] -> [M, out] with autocast's fp16 rounding points."""
+    h = _h(inp)
+    for w, b in weights:
+        h = mlp_linear_relu_half(h, w, b)
+    return h
+
+
+def psf_pack_half(raw, ks):
+    """PSFNet.pred's tail in torch's fp16 arithmetic (psfnet.py:326-333): raw [2P, >= ks*ks] (row 2p left, 2p + 1 right,
+    unflipped) -> [P, 2, ks, ks]: flip the right kernels along the last axis, stack, divide by sum(-1).sum(-1) + 1e-9.
+    sum(-1) accumulates in float32 and rounds to fp16 at each of the two reductions; the quotient is rounded once.
+    All-zero kernels are returned as zeros (the reference's CUDA run yields NaN = 0/0 there, its CPU run 0)."""
+    raw = _h(np.asarray(raw)[:, :ks * ks]).reshape(-1, 2, ks, ks).copy()
+    raw[:, 1] = raw[:, 1, :, ::-1]
+    rows = np.zeros(raw.shape[:3], F32)
+    for v in range(ks):                                                     # sequential float32 accumulation
+        rows = rows + raw[..., v]
+    rows = _h(rows)
+    tot = np.zeros(raw.shape[:2], F32)
+    for u in range(ks):
+        tot = tot + rows[..., u]
+    den = _h(_h(tot) + F32(1e-9))[..., None, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = np.where(den > 0, raw / den, F32(0))
+    return _h(out)
+
+
+def psfnet_render_half(weights, img, depth_z, ks, tone=3):
+    """PSFNet.render(train=False) as the reference's CUDA run computes it (psfnet.py:681-713): coordinate grid, fp16 MLP
+    for both sides, pack, degamma, fp16 gather-convolution, gamma, clip.  img [B,3,H,W], depth_z = depth2z(depth) [B,H,W]."""
+    b, c, h, w = img.shape
+    xs, ys = _torch_linspace(-1, 1, w), _torch_linspace(1, -1, h)
+    rows = mlp_input_rows(xs, ys, depth_z, 0, b, 0, h)
+    psf = psf_pack_half(mlp_forward_half(weights, rows), ks).reshape(b, h, w, 2, ks, ks)
+    rl, rr = render_local_psf(degamma(img) if tone & 1 else img, psf, ks)
+    out = np.concatenate((rl, rr), 1)
+    return np.clip(gamma(out), 0, 1) if tone & 2 else out

@@ -67,6 +67,9 @@ def lib():
     L.sdirt_pupil_sort.argtypes = [vp, i64, dbl, vp, vp, i64, vp]
     L.sdirt_splat_rays.argtypes = [vp, vp, vp, i64, i64, vp, cint, dbl, C.POINTER(DPParams), vp, vp, vp, i64, vp]
     L.sdirt_render_local_psf.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
+    L.sdirt_render_local_psf_rows.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
+    L.sdirt_mlp_input_layer.argtypes = [vp, vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, cint, vp, vp]
+    L.sdirt_psf_pack.argtypes = [vp, i64, cint, cint, vp, vp]
     L.sdirt_fp32_peak_probe.argtypes = [vp, cint, cint, cint, vp]
     _lib = L
     return L
@@ -290,6 +293,57 @@ def render_local_psf(img, psf, ks, tone=0):
                                         b, c, h, w, int(ks), int(tone), _dev(rl, "out_l"), _dev(rr, "out_r"),
                                         _stream(img)))
     return rl, rr
+
+
+def render_local_psf_rows(img, psf_rows, ks, row0, out_l, out_r, tone=0):
+    """Rows [row0, row0 + n_rows) of every image: img [B,C,H,W] float32, psf_rows [B,n_rows,W,2,ks,ks] float32/float16,
+    written into the whole-image outputs out_l / out_r [B,C,H,W]."""
+    b, c, h, w = img.shape
+    n_rows = psf_rows.shape[1]
+    if psf_rows.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("sdirt_engine: psf must be float32 or float16")
+    if psf_rows.dim() != 6 or psf_rows.numel() != b * n_rows * w * 2 * ks * ks:
+        raise RuntimeError("sdirt_engine: psf_rows must be [B,n_rows,W,2,ks,ks]")
+    if out_l.shape != img.shape or out_r.shape != img.shape:
+        raise RuntimeError("sdirt_engine: outputs must have the image's shape")
+    _check(lib().sdirt_render_local_psf_rows(_dev(img, "img"), _dev(psf_rows, "psf_rows", psf_rows.dtype),
+                                             int(psf_rows.dtype == torch.float16), b, c, h, w, int(row0), int(n_rows), int(ks),
+                                             int(tone), _dev(out_l, "out_l"), _dev(out_r, "out_r"), _stream(img)))
+    return out_l, out_r
+
+
+def mlp_input_layer(xs, ys, z, b0, nb, row0, n_rows, w1, b1, out=None):
+    """First activation of the PSF MLP for the pixels of images [b0, b0+nb), rows [row0, row0+n_rows): out [2P, n1] float16,
+    row 2p = left (x, y, z), row 2p+1 = right (-x, y, z), p = ((b-b0)*n_rows + (y-row0))*W + x.  xs [W], ys [H], z [B,H,W]
+    float32; w1 [n1,3], b1 [n1] float16."""
+    bsz, h, w = z.shape
+    n1 = w1.shape[0]
+    rows = 2 * nb * n_rows * w
+    if out is None:
+        out = torch.empty((rows, n1), device=z.device, dtype=torch.float16)
+    elif out.shape != (rows, n1):
+        raise RuntimeError("sdirt_engine: `out` must be [2 * nb * n_rows * W, n1]")
+    if xs.numel() != w or ys.numel() != h or w1.shape != (n1, 3) or b1.numel() != n1:
+        raise RuntimeError("sdirt_engine: mlp_input_layer shapes do not match")
+    _check(lib().sdirt_mlp_input_layer(_dev(xs, "xs"), _dev(ys, "ys"), _dev(z, "z"), bsz, h, w, int(b0), int(nb), int(row0),
+                                       int(n_rows), _dev(w1, "w1", torch.float16), _dev(b1, "b1", torch.float16), n1,
+                                       _dev(out, "out", torch.float16), _stream(z)))
+    return out
+
+
+def psf_pack(raw, ks, out=None):
+    """raw [2P, ld] float16 (ld >= ks*ks; row 2p left, 2p+1 right, unflipped) -> [P,2,ks,ks] float16 normalised kernels
+    (PSFNet.pred: flip the right side, stack, divide by sum + 1e-9)."""
+    rows, ld = raw.shape
+    if rows % 2:
+        raise RuntimeError("sdirt_engine: psf_pack needs an even number of rows (left / right pairs)")
+    if out is None:
+        out = torch.empty((rows // 2, 2, ks, ks), device=raw.device, dtype=torch.float16)
+    elif out.numel() != rows * ks * ks:
+        raise RuntimeError("sdirt_engine: `out` must hold [P,2,ks,ks]")
+    _check(lib().sdirt_psf_pack(_dev(raw, "raw", torch.float16), rows // 2, int(ld), int(ks), _dev(out, "out", torch.float16),
+                                _stream(raw)))
+    return out
 
 
 def fp32_peak_probe(device, blocks, threads, iters):

@@ -81,13 +81,13 @@ struct RenderGeom {
 
 template <int KS, typename PsfT>
 __global__ void __launch_bounds__(RP_WARPS * 32, 3)
-render_pairs_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf, int B, int H, int W, int tone,
+render_pairs_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf, int B, int H, int W, int row0, int nrw, int tone,
                     float *__restrict__ out_l, float *__restrict__ out_r) {
     using G = RenderGeom<KS>;
     extern __shared__ unsigned rp_smem[];               // [2 copies][C][TH][RW] words of two fp16 each
     __half *s0h = reinterpret_cast<__half *>(rp_smem);  // copy 0 addressed by element
     constexpr int pad = (KS - 1) / 2;
-    const int b = blockIdx.z, y0 = blockIdx.y * RP_TH, x0 = blockIdx.x * RP_TW;
+    const int b = blockIdx.z, y0 = row0 + blockIdx.y * RP_TH, x0 = blockIdx.x * RP_TW;
 
     // ---- stage the mirrored tile: copy 0 element (r, m) = image(y0 + r - pad, x0 + (TW-1-m) - pad), replicate-padded
     for (int i = threadIdx.x; i < RP_C * G::TH * 2 * G::RW; i += blockDim.x) {
@@ -148,11 +148,11 @@ render_pairs_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf,
     // ---- pixels: warp w owns tile rows w, w + 8 -----------------------------------------------------------------------
     for (int ly = warp; ly < RP_TH; ly += RP_WARPS) {
         const int y = y0 + ly;
-        if (y >= H) break;
+        if (y >= row0 + nrw) break;
         for (int lx = 0; lx < RP_TW; ++lx) {
             const int x = x0 + lx;
             if (x >= W) break;
-            const PsfT *kp = psf + (((int64_t)b * H + y) * W + x) * (2 * KS * KS);
+            const PsfT *kp = psf + (((int64_t)b * nrw + (y - row0)) * W + x) * (2 * KS * KS);
             const int base = ly * G::RW - (lx >> 1);
             const bool odd = lx & 1;
             float acc[2][RP_C];
@@ -205,16 +205,16 @@ render_pairs_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf,
 }
 
 template <int KS>
-static int launch_render_pairs(const float *img, const void *psf, int psf_is_half, int B, int H, int W, int tone,
+static int launch_render_pairs(const float *img, const void *psf, int psf_is_half, int B, int H, int W, int row0, int nrw, int tone,
                                float *out_l, float *out_r, cudaStream_t st) {
     using G = RenderGeom<KS>;
-    dim3 grid((W + RP_TW - 1) / RP_TW, (H + RP_TH - 1) / RP_TH, B);
+    dim3 grid((W + RP_TW - 1) / RP_TW, (nrw + RP_TH - 1) / RP_TH, B);
     if (psf_is_half) {
         CUDA_TRY(cudaFuncSetAttribute(render_pairs_kernel<KS, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-        render_pairs_kernel<KS, __half><<<grid, RP_WARPS * 32, G::SMEM_BYTES, st>>>(img, (const __half *)psf, B, H, W, tone, out_l, out_r);
+        render_pairs_kernel<KS, __half><<<grid, RP_WARPS * 32, G::SMEM_BYTES, st>>>(img, (const __half *)psf, B, H, W, row0, nrw, tone, out_l, out_r);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(render_pairs_kernel<KS, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-        render_pairs_kernel<KS, float><<<grid, RP_WARPS * 32, G::SMEM_BYTES, st>>>(img, (const float *)psf, B, H, W, tone, out_l, out_r);
+        render_pairs_kernel<KS, float><<<grid, RP_WARPS * 32, G::SMEM_BYTES, st>>>(img, (const float *)psf, B, H, W, row0, nrw, tone, out_l, out_r);
     }
     return check_launch("render_pairs_kernel");
 }
@@ -265,7 +265,7 @@ struct StreamGeom {
 
 template <int KS, typename PsfT, int SEG>
 __global__ void __launch_bounds__(RS_WARPS * 32, 1)
-render_stream_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf, int B, int H, int W, int tone,
+render_stream_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf, int B, int H, int W, int row0, int nrw, int tone,
                      float *__restrict__ out_l, float *__restrict__ out_r) {
     using SG = StreamGeom<KS, PsfT, SEG>;
     using G = typename SG::G;
@@ -274,8 +274,8 @@ render_stream_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf
     __half *s0h = reinterpret_cast<__half *>(tile);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(rs_raw + SG::BAR_OFF), *empty = full + RS_STAGES;
     constexpr int pad = (KS - 1) / 2;
-    const int b = blockIdx.z, y0 = blockIdx.y * RP_TH, x0 = blockIdx.x * SEG;
-    const int nrows = min(RP_TH, H - y0);
+    const int b = blockIdx.z, y0 = row0 + blockIdx.y * RP_TH, x0 = blockIdx.x * SEG;
+    const int nrows = min(RP_TH, row0 + nrw - y0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) {
@@ -286,7 +286,7 @@ render_stream_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf
     auto issue = [&](int row) {
         const int st = row % RS_STAGES;
         mbar_expect_tx(full + st, SG::STAGE_BYTES);
-        bulk_g2s(rs_raw + st * SG::STAGE_BYTES, psf + (((int64_t)b * H + (y0 + row)) * W + x0) * (2 * KS * KS), SG::STAGE_BYTES, full + st);
+        bulk_g2s(rs_raw + st * SG::STAGE_BYTES, psf + (((int64_t)b * nrw + (y0 - row0 + row)) * W + x0) * (2 * KS * KS), SG::STAGE_BYTES, full + st);
     };
     if (threadIdx.x == 0)
         for (int row = 0; row < min(RS_STAGES, nrows); ++row) issue(row);
@@ -474,7 +474,7 @@ __device__ __forceinline__ void lane_row(const unsigned char *kb, const unsigned
 // also issues the bulk copies.  Everything between the roles is an mbarrier: compute warps never meet a CTA-wide barrier in the row loop.
 template <int KS>
 __global__ void __launch_bounds__((LaneGeom<KS>::NW + 2) * 32, 1)
-render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ psf, int B, int H, int W, int tone,
+render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ psf, int B, int H, int W, int row0, int nrw, int tone,
                     float *__restrict__ out_l, float *__restrict__ out_r) {
     using G = LaneGeom<KS>;
     extern __shared__ __align__(128) unsigned char rl_raw[];
@@ -484,8 +484,8 @@ render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ ps
     unsigned long long *full = reinterpret_cast<unsigned long long *>(rl_raw + G::BAR_OFF), *empty = full + RS_STAGES;
     unsigned long long *pfull = empty + RS_STAGES, *pempty = pfull + RL_PBUF;
     constexpr int pad = (KS - 1) / 2, SEG = G::SEG, CHB = 4 * G::CHW;
-    const int b = blockIdx.z, y0 = blockIdx.y * RP_TH, x0 = blockIdx.x * SEG;
-    const int nrows = min(RP_TH, H - y0);
+    const int b = blockIdx.z, y0 = row0 + blockIdx.y * RP_TH, x0 = blockIdx.x * SEG;
+    const int nrows = min(RP_TH, row0 + nrw - y0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) {
@@ -497,7 +497,7 @@ render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ ps
     auto issue = [&](int row) {
         const int st = row % RS_STAGES;
         mbar_expect_tx(full + st, G::STAGE_BYTES);
-        bulk_g2s(rl_raw + st * G::STAGE_BYTES, psf + (((int64_t)b * H + (y0 + row)) * W + x0) * (2 * KS * KS), G::STAGE_BYTES, full + st);
+        bulk_g2s(rl_raw + st * G::STAGE_BYTES, psf + (((int64_t)b * nrw + (y0 - row0 + row)) * W + x0) * (2 * KS * KS), G::STAGE_BYTES, full + st);
     };
     if (warp == G::NW && lane == 0)
         for (int row = 0; row < min(RS_STAGES, nrows); ++row) issue(row);
@@ -603,39 +603,39 @@ render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ ps
 }
 
 template <int KS>
-static int launch_render_lanes(const float *img, const __half *psf, int B, int H, int W, int tone, float *out_l, float *out_r,
-                               cudaStream_t st) {
+static int launch_render_lanes(const float *img, const __half *psf, int B, int H, int W, int row0, int nrw, int tone,
+                               float *out_l, float *out_r, cudaStream_t st) {
     using G = LaneGeom<KS>;
-    dim3 grid(W / G::SEG, (H + RP_TH - 1) / RP_TH, B);
+    dim3 grid(W / G::SEG, (nrw + RP_TH - 1) / RP_TH, B);
     CUDA_TRY(cudaFuncSetAttribute(render_lanes_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    render_lanes_kernel<KS><<<grid, (G::NW + 2) * 32, G::SMEM_BYTES, st>>>(img, psf, B, H, W, tone, out_l, out_r);
+    render_lanes_kernel<KS><<<grid, (G::NW + 2) * 32, G::SMEM_BYTES, st>>>(img, psf, B, H, W, row0, nrw, tone, out_l, out_r);
     return check_launch("render_lanes_kernel");
 }
 
 // W % SEG == 0 and 16-byte aligned rows are what the bulk copies need; anything else runs the direct kernel.
 template <int KS>
-static int launch_render(const float *img, const void *psf, int psf_is_half, int B, int H, int W, int tone,
+static int launch_render(const float *img, const void *psf, int psf_is_half, int B, int H, int W, int row0, int nrw, int tone,
                          float *out_l, float *out_r, cudaStream_t st) {
     if (psf_is_half && W % 32 == 0 && ((uintptr_t)psf & 15) == 0 && LaneGeom<KS>::SMEM_BYTES <= 227 * 1024)
-        return launch_render_lanes<KS>(img, (const __half *)psf, B, H, W, tone, out_l, out_r, st);
+        return launch_render_lanes<KS>(img, (const __half *)psf, B, H, W, row0, nrw, tone, out_l, out_r, st);
     if (psf_is_half && W % 32 == 0 && ((uintptr_t)psf & 15) == 0) {
         using SG = StreamGeom<KS, __half, 32>;
         if (SG::SMEM_BYTES <= 227 * 1024) {
-            dim3 grid(W / 32, (H + RP_TH - 1) / RP_TH, B);
+            dim3 grid(W / 32, (nrw + RP_TH - 1) / RP_TH, B);
             CUDA_TRY(cudaFuncSetAttribute(render_stream_kernel<KS, __half, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG::SMEM_BYTES));
-            render_stream_kernel<KS, __half, 32><<<grid, RS_WARPS * 32, SG::SMEM_BYTES, st>>>(img, (const __half *)psf, B, H, W, tone, out_l, out_r);
+            render_stream_kernel<KS, __half, 32><<<grid, RS_WARPS * 32, SG::SMEM_BYTES, st>>>(img, (const __half *)psf, B, H, W, row0, nrw, tone, out_l, out_r);
             return check_launch("render_stream_kernel");
         }
     }
     if (!psf_is_half && W % 16 == 0 && ((uintptr_t)psf & 15) == 0) {
         using SG = StreamGeom<KS, float, 16>;
         if (SG::SMEM_BYTES <= 227 * 1024) {
-            dim3 grid(W / 16, (H + RP_TH - 1) / RP_TH, B);
+            dim3 grid(W / 16, (nrw + RP_TH - 1) / RP_TH, B);
             CUDA_TRY(cudaFuncSetAttribute(render_stream_kernel<KS, float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG::SMEM_BYTES));
-            render_stream_kernel<KS, float, 16><<<grid, RS_WARPS * 32, SG::SMEM_BYTES, st>>>(img, (const float *)psf, B, H, W, tone, out_l, out_r);
+            render_stream_kernel<KS, float, 16><<<grid, RS_WARPS * 32, SG::SMEM_BYTES, st>>>(img, (const float *)psf, B, H, W, row0, nrw, tone, out_l, out_r);
             return check_launch("render_stream_kernel");
         }
     }
-    return launch_render_pairs<KS>(img, psf, psf_is_half, B, H, W, tone, out_l, out_r, st);
+    return launch_render_pairs<KS>(img, psf, psf_is_half, B, H, W, row0, nrw, tone, out_l, out_r, st);
 }
 

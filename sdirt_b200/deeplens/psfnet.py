@@ -150,14 +150,111 @@ class PSFNet(Lensgroup):
         render += noise_map * weight_map
         return render
 
+    # ---- banded render: the per-pixel PSF tensor only ever exists for one band of rows -------------------
+    render_band_rows = 16            # rows per band (the render kernels' tile height)
+    render_band_pixels = 98304       # pixels per band batch: images are grouped until a band holds about this many
+    render_overlap = True            # pack + convolve band i on a second stream while the GEMMs of band i + 1 run
+
+    def _render_post_stream(self, device):
+        st = getattr(self, "_post_stream", None)
+        if st is None or st.device != torch.device(device):
+            st = self._post_stream = torch.cuda.Stream(device=device)
+        return st
+
+    def _mlp_half_layers(self):
+        """fp16 copies of the MLP's Linear layers, as CUDA autocast casts them on every call (psfnet_arch.py:52); cached on
+        the parameters' versions.  The last layer's N is padded to a multiple of 8 (16-byte rows for cuBLAS)."""
+        lin = [m for m in self.psfnet.net if isinstance(m, nn.Linear)]
+        key = tuple((m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(), m.bias._version) for m in lin)
+        cache = getattr(self, "_mlp_half_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        first = (lin[0].weight.detach().half().contiguous(), lin[0].bias.detach().half().contiguous())
+        chain = []
+        for i, m in enumerate(lin[1:]):
+            w, b = m.weight.detach().half(), m.bias.detach().half()
+            if i == len(lin) - 2 and w.shape[0] % 8:
+                padn = 8 - w.shape[0] % 8
+                w = torch.cat((w, w.new_zeros(padn, w.shape[1])), 0)
+                b = torch.cat((b, b.new_zeros(padn)), 0)
+            chain.append((w.contiguous().t(), b.contiguous()))
+        layers = (first, chain)
+        self._mlp_half_cache = (key, layers)
+        return layers
+
     @torch.no_grad()
     def render(self, img, depth, foc_dist, train=False):
         """[N, 6, H, W] dual-pixel image (left RGB, right RGB) from an all-in-focus image [N, 3, H, W] and a depth
-        map [N, 1, H, W] in negative millimetres (psfnet.py:645-714).  degamma, the per-pixel gather-convolution,
-        gamma and the final clip run in ONE engine kernel."""
+        map [N, 1, H, W] in negative millimetres (psfnet.py:645-714).
+
+        The reference builds the per-pixel PSF tensor [N,H,W,2,ks,ks] of the whole batch (`pred`) and then convolves.
+        Here the image is walked in bands of rows: coordinate grid + first Linear (engine kernel), the 512-wide GEMM chain
+        (cuBLAS, bias + ReLU in the GEMM epilogue), flip / stack / normalise (engine kernel), degamma + gather-convolution +
+        gamma + clip (engine kernel) -- the PSFs of a band stay in the L2 between their producer and their consumer, and
+        memory use does not grow with the image."""
         if img.dim() != 4:
             raise NotImplementedError("PSFNet.render expects a batched [N, C, H, W] image")
+        if not img.is_cuda:
+            raise RuntimeError("PSFNet.render: the engine has no CPU path (img must be a CUDA tensor)")
         depth = depth + self.d_sensor                                     # the reference's d_sensor fix, :658
+        N, C, H, W = img.shape
+        ks = self.kernel_size
+        z = self.depth2z(depth).reshape(N, H, W).float().contiguous()
+        xs = torch.linspace(-1, 1, W).to(img.device)                      # made on the host, as the reference does (:684-688)
+        ys = torch.linspace(1, -1, H).to(img.device)
+        (w1, b1), chain = self._mlp_half_layers()
+        img32 = img.float().contiguous()
+        rl, rr = torch.empty_like(img32), torch.empty_like(img32)
+        rows = max(1, min(int(self.render_band_rows), H))
+        nb = max(1, min(N, int(self.render_band_pixels) // (rows * W)))
+        tone = 1 if train else 3
+        # Two streams: the GEMM chain of band i + 1 (tensor cores) runs while band i is packed and convolved (memory pipes).
+        # raw / psf buffers are double-buffered by hand so that no tensor crosses streams through the caching allocator.
+        main = torch.cuda.current_stream(img.device)
+        post = self._render_post_stream(img.device) if self.render_overlap else main
+        n_out = chain[-1][0].shape[1]
+        max_px = nb * rows * W
+        raw = [torch.empty((2 * max_px, n_out), device=img.device, dtype=torch.float16) for _ in range(2)]
+        psf = [torch.empty((max_px, 2, ks, ks), device=img.device, dtype=torch.float16) for _ in range(2)]
+        raw_ready = [torch.cuda.Event() for _ in range(2)]
+        raw_free = [None, None]
+        post.wait_stream(main)                                             # img32 / z / outputs are ready for the post stream
+        i = 0
+        for b0 in range(0, N, nb):
+            nbb = min(nb, N - b0)
+            for y0 in range(0, H, rows):
+                nr = min(rows, H - y0)
+                px = nbb * nr * W
+                k = i & 1
+                h = E.mlp_input_layer(xs, ys, z, b0, nbb, y0, nr, w1, b1)
+                for wt, b in chain[:-1]:
+                    h = torch._addmm_activation(b, h, wt)                 # relu(h @ W^T + b), fp16 in / fp32 accumulate / fp16 out
+                if raw_free[k] is not None:
+                    main.wait_event(raw_free[k])                          # band i - 2 has been packed out of this buffer
+                torch._addmm_activation(chain[-1][1], h, chain[-1][0], out=raw[k][:2 * px])
+                raw_ready[k].record(main)
+                with torch.cuda.stream(post):
+                    post.wait_event(raw_ready[k])
+                    E.psf_pack(raw[k][:2 * px], ks, out=psf[k][:px])
+                    if post is not main:
+                        raw_free[k] = torch.cuda.Event()
+                        raw_free[k].record(post)
+                    E.render_local_psf_rows(img32[b0:b0 + nbb], psf[k][:px].view(nbb, nr, W, 2, ks, ks), ks, y0,
+                                            rl[b0:b0 + nbb], rr[b0:b0 + nbb], tone=tone)
+                i += 1
+        main.wait_stream(post)
+        render = torch.cat((rl, rr), dim=1)
+        if train:                                                          # noise sits between gamma and clip
+            render = self.gamma(render)
+            render = self.noise(render, img.shape)
+            render = torch.clip(render, 0.0, 1.0)
+        return render
+
+    @torch.no_grad()
+    def render_via_pred(self, img, depth, foc_dist, train=False):
+        """The reference's own order of operations (psfnet.py:681-713): `pred` for every pixel of the batch, then one
+        convolution over the whole tensor.  Kept as the memory-hungry comparison path for tests and benchmarks."""
+        depth = depth + self.d_sensor
         N, C, H, W = img.shape
         z = self.depth2z(depth).squeeze(1)
         x, y = torch.meshgrid(torch.linspace(-1, 1, W), torch.linspace(1, -1, H), indexing="xy")
@@ -168,7 +265,7 @@ class PSFNet(Lensgroup):
             psf = psf.float()
         rl, rr = E.render_local_psf(img.float().contiguous(), psf.contiguous(), self.kernel_size, tone=1 if train else 3)
         render = torch.cat((rl, rr), dim=1)
-        if train:                                                          # noise sits between gamma and clip
+        if train:
             render = self.gamma(render)
             render = self.noise(render, img.shape)
             render = torch.clip(render, 0.0, 1.0)

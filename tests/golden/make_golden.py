@@ -291,8 +291,43 @@ def golden_render():
     np.savez_compressed(os.path.join(HERE, "render.npz"), **out)
 
 
+def golden_predhalf():
+    """PSFNet.pred / render with the MLP in fp16, i.e. the arithmetic of the reference's CUDA run (`@autocast()` on
+    MLP.forward is a no-op on CPU, so the plain CPU run above is fp32).  The reference's own `pred` and `render` lines run
+    unmodified; only `lens.psfnet` is wrapped so that the seeded MLP computes in half precision on CPU."""
+    torch.manual_seed(5)
+    lens = dl.PSFNet(LENSES["rf50mm"], sensor_res=(16, 24), kernel_size=21, device="cpu")
+    mlp32 = lens.psfnet
+    mlp16 = mlp32.half()                                   # in-place conversion of the seeded weights
+
+    class HalfMLP(torch.nn.Module):
+        def forward(self, inp):
+            return mlp16(inp.half())
+    half_mlp = HalfMLP()
+    lens.psfnet = half_mlp
+    torch.manual_seed(6)
+    img = torch.rand(2, 3, 16, 24)
+    depth = -(torch.rand(2, 1, 16, 24) * 9750 + 250)
+    foc = torch.tensor([-1000.0, -1000.0])
+    out = {"img": img.numpy(), "depth": depth.numpy(), "foc": foc.numpy()}
+    out["render_out"] = lens.render(img, depth, foc).float().numpy()
+    x, y = torch.meshgrid(torch.linspace(-1, 1, 24), torch.linspace(1, -1, 16), indexing="xy")
+    z = lens.depth2z(depth + lens.d_sensor).squeeze(1)
+    o = torch.stack((x[None].repeat(2, 1, 1), y[None].repeat(2, 1, 1), z), -1).float()
+    out["z"] = z.numpy()
+    raw_l = half_mlp(o.clone())
+    on = o.clone()
+    on[..., 0] = -on[..., 0]
+    raw_r = half_mlp(on)
+    out["raw_l"], out["raw_r"] = raw_l.detach().numpy(), raw_r.detach().numpy()                       # [2,16,24,21,21] fp16, right unflipped
+    out["psf"] = lens.pred(o.clone()).detach().numpy()                                        # [2,16,24,2,21,21] fp16
+    h1 = torch.relu(torch.nn.functional.linear(o.half(), mlp16.net[0].weight, mlp16.net[0].bias))
+    out["h1_l"] = h1.detach().numpy()                                                         # first activation, left rows
+    np.savez_compressed(os.path.join(HERE, "predhalf.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["setup", "trace", "dp", "psf", "psf2m", "render"]
+    which = sys.argv[1:] or ["setup", "trace", "dp", "psf", "psf2m", "render", "predhalf"]
     for w in which:
         globals()[f"golden_{w}"]()
         print("wrote", w)

@@ -192,3 +192,51 @@ def test_psfnet_fitting_loop(tmp_path, lenses):
         lens.numerics = None
     assert len(hist) == 5 and all(np.isfinite(hist))
     assert (tmp_path / "iter4_PSFNet_mlp.pkl").exists()
+
+
+def test_render_banded_vs_reference_half(golden):
+    """PSFNet.render (banded: engine kernels around the cuBLAS GEMM chain) against the reference's own render() run with
+    its MLP in fp16 (tests/golden/predhalf.npz, i.e. the arithmetic of the reference's CUDA path), against the oracle's
+    restatement, and against the unbanded route through `pred`."""
+    from sdirt_b200.deeplens import PSFNet
+    from oracle import dp_oracle as O
+    from test_oracle_golden import seeded_mlp_weights
+    g = golden("predhalf")
+    torch.manual_seed(5)
+    lens = PSFNet(lens_path("rf50mm"), sensor_res=(16, 24), kernel_size=21, device=DEV)
+    img, depth, foc = (torch.from_numpy(g[k]).to(DEV) for k in ("img", "depth", "foc"))
+    out = lens.render(img, depth, foc)
+    assert out.shape == (2, 6, 16, 24)
+    ref = g["render_out"]
+    assert np.abs(out.cpu().numpy() - ref).max() < 2e-3                  # a few fp16 ulps of a [0, 1] image
+    want = O.psfnet_render_half(seeded_mlp_weights(), g["img"], g["z"], 21)
+    assert np.abs(out.cpu().numpy() - want).max() < 2e-3
+    # bands of 5 rows, one image at a time == one band
+    lens.render_band_rows, lens.render_band_pixels = 5, 1
+    try:
+        out5 = lens.render(img, depth, foc)
+    finally:
+        del lens.render_band_rows, lens.render_band_pixels
+    assert torch.equal(out5, out)
+    via = lens.render_via_pred(img, depth, foc)
+    assert (out - via).abs().max().item() < 2e-3
+
+
+def test_render_banded_large_and_train():
+    """A 64 x 96 image batch through several bands and band batches; train=True adds noise between gamma and clip."""
+    from sdirt_b200.deeplens import PSFNet
+    torch.manual_seed(2)
+    lens = PSFNet(lens_path("rf35mm"), sensor_res=(64, 96), kernel_size=11, device=DEV)
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    img = torch.rand((3, 3, 64, 96), device=DEV, generator=gen)
+    depth = -(torch.rand((3, 1, 64, 96), device=DEV, generator=gen) * 9000 + 300)
+    foc = torch.full((3,), -1000.0, device=DEV)
+    lens.render_band_pixels = 2 * 16 * 96
+    out = lens.render(img, depth, foc)
+    via = lens.render_via_pred(img, depth, foc)
+    assert out.shape == (3, 6, 64, 96) and torch.isfinite(out).all()
+    assert (out - via).abs().max().item() < 2e-3
+    np.random.seed(0)
+    tr = lens.render(img, depth, foc, train=True)
+    assert tr.shape == out.shape and float(tr.min()) >= 0.0 and float(tr.max()) <= 1.0
+    assert (tr - out).abs().mean().item() > 1e-4                          # noise was added

@@ -542,3 +542,67 @@ def test_splat_rays_lanes_kernel_matches_point_kernel():
         assert float(L2.sum()) > 1000
         np.testing.assert_allclose(L.cpu().numpy(), L2.cpu().numpy(), rtol=3e-5, atol=3e-5)
         np.testing.assert_allclose(R.cpu().numpy(), R2.cpu().numpy(), rtol=3e-5, atol=3e-5)
+
+
+# ---- the two ends of PSFNet.pred inside the banded render (csrc/psfnet_path.cuh) ---------------------------------------
+def test_mlp_input_layer_vs_oracle(golden):
+    from sdirt_b200 import _engine as E
+    from test_oracle_golden import half_ulps, seeded_mlp_weights
+    g = golden("predhalf")
+    w1, b1 = seeded_mlp_weights()[0]
+    xs, ys = O._torch_linspace(-1, 1, 24), O._torch_linspace(1, -1, 16)
+    z = g["z"]
+    for (b0, nb, r0, nr) in ((0, 2, 0, 16), (1, 1, 5, 7), (0, 1, 15, 1)):
+        got = E.mlp_input_layer(cu(xs), cu(ys), cu(z), b0, nb, r0, nr, torch.from_numpy(w1).to(DEV).half(), torch.from_numpy(b1).to(DEV).half())
+        want = O.mlp_linear_relu_half(O._h(O.mlp_input_rows(xs, ys, z, b0, nb, r0, nr)), w1, b1)
+        assert got.shape == want.shape
+        u = half_ulps(got.float().cpu().numpy(), want)
+        assert u.max() <= 1 and (u == 0).mean() > 0.999
+    # the whole-window call against torch's fp16 Linear + ReLU on the reference's own coordinate grid (left rows)
+    got = E.mlp_input_layer(cu(xs), cu(ys), cu(z), 0, 2, 0, 16, torch.from_numpy(w1).to(DEV).half(), torch.from_numpy(b1).to(DEV).half())
+    u = half_ulps(got.float().cpu().numpy()[0::2].reshape(2, 16, 24, -1), g["h1_l"])
+    assert u.max() <= 1 and (u == 0).mean() > 0.999
+
+
+def test_psf_pack_vs_oracle_and_reference(golden):
+    from sdirt_b200 import _engine as E
+    from test_oracle_golden import half_ulps
+    g = golden("predhalf")
+    raw = np.stack((g["raw_l"].reshape(-1, 441), g["raw_r"].reshape(-1, 441)), 1).reshape(-1, 441)
+    ref = g["psf"].astype(np.float32).reshape(-1, 2, 21, 21)
+    ok = np.isfinite(ref).all((-1, -2))
+    for pad in (0, 7):
+        rawp = np.concatenate((raw, np.full((raw.shape[0], pad), 3.0, np.float16)), 1) if pad else raw
+        got = E.psf_pack(torch.from_numpy(np.ascontiguousarray(rawp)).to(DEV), 21).float().cpu().numpy()
+        np.testing.assert_array_equal(got, O.psf_pack_half(rawp, 21))          # same rounding points: bit-identical
+        u = half_ulps(got[ok], ref[ok])
+        assert u.max() <= 1 and (u == 0).mean() > 0.999                         # torch's own fp16 sum / divide
+        assert (got[~ok] == 0).all()
+    # other window sizes, ragged row counts, an all-zero kernel
+    rng = np.random.default_rng(3)
+    for ks, n in ((7, 33), (11, 5), (31, 2), (33, 3)):
+        r = np.maximum(rng.normal(0.2, 1.0, (2 * n, ks * ks + 3)), 0).astype(np.float16)
+        r[1] = 0
+        got = E.psf_pack(torch.from_numpy(r).to(DEV), ks).float().cpu().numpy()
+        np.testing.assert_array_equal(got, O.psf_pack_half(r, ks))
+        assert (got[0, 1] == 0).all()
+
+
+def test_render_rows_equals_whole_image():
+    """Bands of rows written into the whole-image outputs are bit-identical to one whole-image call (every kernel variant:
+    lanes / streamed fp32 / pairs / generic)."""
+    from sdirt_b200 import _engine as E
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    for (B, C, H, W, ks, dt) in ((2, 3, 40, 64, 21, torch.float16), (1, 3, 37, 48, 21, torch.float32), (1, 3, 23, 40, 7, torch.float16),
+                                 (1, 3, 19, 21, 11, torch.float16), (1, 2, 20, 33, 5, torch.float32)):
+        img = torch.rand((B, C, H, W), device=DEV, generator=gen)
+        psf = torch.rand((B, H, W, 2, ks, ks), device=DEV, generator=gen) ** 3
+        psf = (psf / psf.sum((-1, -2), keepdim=True)).to(dt).contiguous()
+        rl, rr = E.render_local_psf(img, psf, ks, tone=3)
+        bl, br = torch.full_like(img, -1.0), torch.full_like(img, -1.0)
+        cuts = sorted({0, min(16, H), min(21, H), H})
+        for y0, y1 in zip(cuts[:-1], cuts[1:]):
+            E.render_local_psf_rows(img, psf[:, y0:y1].contiguous(), ks, y0, bl, br, tone=3)
+        assert torch.equal(bl, rl) and torch.equal(br, rr)
+    with pytest.raises(RuntimeError):
+        E.render_local_psf_rows(img, psf[:, :4].contiguous(), ks, H - 2, bl, br)

@@ -257,3 +257,76 @@ def test_render_local_psf(golden, ks):
     np.testing.assert_allclose(rl, g[f"ks{ks}_rl"], rtol=1.1e-3, atol=1e-6)
     np.testing.assert_allclose(rr, g[f"ks{ks}_rr"], rtol=1.1e-3, atol=1e-6)
     assert (rl == g[f"ks{ks}_rl"]).mean() > 0.9
+
+
+# ---- PSFNet.pred / render in the arithmetic of the reference's CUDA run (fp16 MLP), tests/golden/predhalf.npz -------
+def seeded_mlp_weights(seed=5, ks=21):
+    """(W, b) of the reference's random-init PSF MLP, recreated from the seed (pinned by test_mlp_matches_reference_init)."""
+    from sdirt_b200.deeplens.psfnet_arch import MLP, initialize_weights
+    torch.manual_seed(seed)
+    net = MLP(in_features=3, out_features=ks ** 2, hidden_features=512, hidden_layers=8)
+    net.apply(initialize_weights)
+    lin = [m for m in net.net if isinstance(m, torch.nn.Linear)]
+    return [(m.weight.detach().numpy(), m.bias.detach().numpy()) for m in lin]
+
+
+def half_ulps(a, b):
+    """Distance in fp16 units in the last place between two arrays of fp16-representable values."""
+    a16, b16 = np.asarray(a).astype(np.float16), np.asarray(b).astype(np.float16)
+    ia, ib = a16.view(np.int16).astype(np.int32), b16.view(np.int16).astype(np.int32)
+    return np.abs(ia - ib)                                                  # all values here are >= 0
+
+
+def test_mlp_input_layer_half(golden):
+    g = golden("predhalf")
+    w = seeded_mlp_weights()
+    xs, ys = O._torch_linspace(-1, 1, 24), O._torch_linspace(1, -1, 16)
+    rows = O.mlp_input_rows(xs, ys, g["z"], 0, 2, 0, 16)
+    assert rows.shape == (2 * 2 * 16 * 24, 3)
+    h1 = O.mlp_linear_relu_half(O._h(rows), *w[0])
+    # left rows against torch's own fp16 Linear + ReLU on the reference's coordinate grid
+    assert half_ulps(h1[0::2].reshape(2, 16, 24, -1), g["h1_l"]).max() <= 1
+    assert (half_ulps(h1[0::2].reshape(2, 16, 24, -1), g["h1_l"]) == 0).mean() > 0.999
+    # right rows: same y, z, mirrored x
+    np.testing.assert_array_equal(rows[1::2, 0], -rows[0::2, 0])
+    np.testing.assert_array_equal(rows[1::2, 1:], rows[0::2, 1:])
+
+
+def test_mlp_forward_half(golden):
+    """The 11-layer fp16 chain: rounding to fp16 after every layer makes the result sensitive to the fp32 accumulation
+    order inside each GEMM, so equality with torch's CPU half GEMM is statistical: a few fp16 ulps, mostly none."""
+    g = golden("predhalf")
+    w = seeded_mlp_weights()
+    xs, ys = O._torch_linspace(-1, 1, 24), O._torch_linspace(1, -1, 16)
+    rows = O.mlp_input_rows(xs, ys, g["z"], 0, 1, 0, 4)                     # 96 pixels: both sides, 192 rows
+    raw = O.mlp_forward_half(w, rows)
+    ref_l = g["raw_l"][0, :4].reshape(-1, 441).astype(np.float32)
+    ref_r = g["raw_r"][0, :4].reshape(-1, 441).astype(np.float32)
+    for got, ref in ((raw[0::2], ref_l), (raw[1::2], ref_r)):
+        scale = ref.max()
+        assert np.abs(got - ref).max() <= 4e-3 * scale
+        assert np.abs(got - ref).mean() <= 2e-4 * scale
+
+
+def test_psf_pack_half(golden):
+    g = golden("predhalf")
+    raw = np.stack((g["raw_l"].reshape(-1, 441), g["raw_r"].reshape(-1, 441)), 1).reshape(-1, 441)
+    psf = O.psf_pack_half(raw, 21).reshape(2, 16, 24, 2, 21, 21)
+    ref = g["psf"].astype(np.float32)
+    ok = np.isfinite(ref).all((-1, -2))                                     # 0/0 kernels are NaN in the reference
+    assert ok.mean() > 0.99
+    u = half_ulps(psf[ok], ref[ok])
+    assert u.max() <= 1 and (u == 0).mean() > 0.999
+    assert (psf[~ok] == 0).all()
+    # padded rows (the GEMM's N rounded up to 448) give the same kernels
+    rawp = np.concatenate((raw, np.full((raw.shape[0], 7), 7.0, np.float16)), 1)
+    np.testing.assert_array_equal(O.psf_pack_half(rawp, 21).reshape(psf.shape), psf)
+
+
+def test_psfnet_render_half(golden):
+    g = golden("predhalf")
+    w = seeded_mlp_weights()
+    out = O.psfnet_render_half(w, g["img"][:1], g["z"][:1], 21)
+    ref = g["render_out"][:1]
+    assert out.shape == ref.shape == (1, 6, 16, 24)
+    assert np.abs(out - ref).max() < 2e-3                                   # a few fp16 ulps of a [0, 1] image
