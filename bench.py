@@ -340,6 +340,22 @@ def run_gpu(args):
               "roofline": {"bound": "hbm", "achieved": rbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                            "frac": rbytes / (ms * 1e-3) / 1e9 / hbm, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
     del psf, img
+    # BASELINE config 4 shape: PSFNet.render end to end (banded: engine kernels around the cuBLAS GEMM chain of the PSF MLP)
+    rlens = PSFNet(lens_file(LENS), sensor_res=(rh, rw), kernel_size=KS, device=dev)
+    img = torch.rand((rb, 3, rh, rw), device=dev, generator=g)
+    low = torch.rand((rb, 1, rh // 64 + 2, rw // 64 + 2), device=dev, generator=g)
+    depth = -(torch.nn.functional.interpolate(low, size=(rh, rw), mode="bilinear", align_corners=False) * 9750 + 250)
+    foc = torch.full((rb,), -1000.0, device=dev)
+    ms = timed(lambda: rlens.render(img, depth, foc), 3)
+    mlp_flop_px = 2 * 2 * (3 * 128 + 128 * 512 + 8 * 512 * 512 + 512 * KS * KS)
+    tpeak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1373.0))
+    render_psfnet = {"metric": "pixels/s, PSFNet.render (coordinate grid -> PSF MLP both sides -> normalise -> degamma -> DP "
+                               "gather-convolution -> gamma -> clip), banded",
+                     "value": rb * rh * rw / (ms * 1e-3), "unit": "pixels/s", "shape": [rb, 3, rh, rw], "ks": KS,
+                     "roofline": {"bound": "tensor", "achieved": rb * rh * rw * mlp_flop_px / (ms * 1e-3) / 1e12, "peak": tpeak,
+                                  "unit": "TFLOP/s", "frac": rb * rh * rw * mlp_flop_px / (ms * 1e-3) / 1e12 / tpeak,
+                                  "note": "9.56 MFLOP/pixel of 16-bit GEMM (cuBLAS) dominate; peak = measured dense 16-bit matmul"}}
+    del img, depth, rlens
 
     # ---- CPU baseline on this box's host cores (bounded sample) --------------------------------------
     cpu = None
@@ -362,6 +378,7 @@ def run_gpu(args):
         "cpu_baseline": cpu,
         "numerics_modes_rays_per_s": modes,
         "render": render,
+        "render_psfnet": render_psfnet,
     }))
     if world > 1:
         dist.destroy_process_group()

@@ -25,6 +25,7 @@
  *                                      PSFNet.degamma / gamma / clip       deeplens/psfnet.py:589-620,706-713
  *   sdirt_mlp_input_layer           <- coordinate grid + first Linear+ReLU deeplens/psfnet.py:681-694; psfnet_arch.py:40-41
  *   sdirt_psf_pack                  <- PSFNet.pred: flip, stack, normalise deeplens/psfnet.py:326-333
+ *   sdirt_gamma_noise_clip          <- PSFNet.gamma / noise / clip (train) deeplens/psfnet.py:605-620, 629-642, 708-713
  *
  * Conventions: every pointer marked "dev" is device memory owned by the caller (a torch CUDA tensor's
  * data_ptr); the library allocates nothing on the device.  All work is enqueued on `stream`
@@ -224,6 +225,13 @@ int sdirt_mlp_input_layer(const float *xs_dev, const float *ys_dev, const float 
                           int b0, int nb, int row0, int n_rows, const void *w1_half_dev, const void *b1_half_dev,
                           int n1, void *out_half_dev, void *stream);
 int sdirt_psf_pack(const void *raw_half_dev, int64_t n_pixels, int ld, int ks, void *psf_half_dev, void *stream);
+
+/* gamma -> sensor noise -> clip(0,1), the tail of PSFNet.render(train=True) (psfnet.py:605-620, 629-642, 708-713), in
+ * place on x_dev[N, 2C, H, W] (the convolved linear image, left channels first).  randn_dev: standard-normal draws of
+ * that shape; noise_range_dev[N]; weight_dev[N, W]: the linspace(range1, range2, W) ramp, read mirrored for the right
+ * channels.  x <- clip(gamma(x) + (randn * noise_range) * weight, 0, 1). */
+int sdirt_gamma_noise_clip(float *x_dev, const float *randn_dev, const float *noise_range_dev, const float *weight_dev,
+                           int N, int C2, int H, int W, void *stream);
 
 /* ---- measurement helper: dependent-free FP32 FMA loop, returns nothing; timed by the caller -------- */
 int sdirt_fp32_peak_probe(float *out_dev, int blocks, int threads, int iters, void *stream);

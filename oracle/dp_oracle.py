@@ -859,3 +859,14 @@ def psfnet_render_half(weights, img, depth_z, ks, tone=3):
     rl, rr = render_local_psf(degamma(img) if tone & 1 else img, psf, ks)
     out = np.concatenate((rl, rr), 1)
     return np.clip(gamma(out), 0, 1) if tone & 2 else out
+
+
+def gamma_noise_clip(x, randn, noise_range, weight):
+    """Tail of PSFNet.render(train=True) (psfnet.py:605-620, 629-642, 708-713): x [N,2C,H,W] linear image -> clip(gamma(x) +
+    (randn * noise_range) * ramp, 0, 1), ramp = weight[n, col] on the left channels and mirrored on the right ones."""
+    x, randn = _f(x), _f(randn)
+    n, c2, h, w = x.shape
+    wl = _f(weight)[:, None, None, :]
+    ramp = np.concatenate((np.broadcast_to(wl, (n, c2 // 2, h, w)), np.broadcast_to(wl[..., ::-1], (n, c2 // 2, h, w))), 1)
+    noise = (randn * _f(noise_range)[:, None, None, None]) * ramp
+    return np.clip(gamma(x) + noise, F32(0), F32(1))

@@ -70,6 +70,7 @@ def lib():
     L.sdirt_render_local_psf_rows.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
     L.sdirt_mlp_input_layer.argtypes = [vp, vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, cint, vp, vp]
     L.sdirt_psf_pack.argtypes = [vp, i64, cint, cint, vp, vp]
+    L.sdirt_gamma_noise_clip.argtypes = [vp, vp, vp, vp, cint, cint, cint, cint, vp]
     L.sdirt_fp32_peak_probe.argtypes = [vp, cint, cint, cint, vp]
     _lib = L
     return L
@@ -344,6 +345,17 @@ def psf_pack(raw, ks, out=None):
     _check(lib().sdirt_psf_pack(_dev(raw, "raw", torch.float16), rows // 2, int(ld), int(ks), _dev(out, "out", torch.float16),
                                 _stream(raw)))
     return out
+
+
+def gamma_noise_clip(x, randn, noise_range, weight):
+    """In place on x [N,2C,H,W] float32: clip(gamma(x) + (randn * noise_range[n]) * ramp, 0, 1); ramp = weight[n, col] for the
+    left channels, weight[n, W-1-col] for the right ones (PSFNet.gamma / noise / clip of render(train=True))."""
+    n, c2, h, w = x.shape
+    if randn.shape != x.shape or noise_range.numel() != n or weight.shape != (n, w):
+        raise RuntimeError("sdirt_engine: gamma_noise_clip shapes do not match")
+    _check(lib().sdirt_gamma_noise_clip(_dev(x, "x"), _dev(randn, "randn"), _dev(noise_range, "noise_range"),
+                                        _dev(weight, "weight"), n, c2, h, w, _stream(x)))
+    return x
 
 
 def fp32_peak_probe(device, blocks, threads, iters):

@@ -156,3 +156,21 @@ psf_pack_kernel(const __half *__restrict__ raw, int64_t n_pix, int ld, int ks_rt
         __syncwarp();
     }
 }
+
+// gamma -> sensor noise -> clip, the tail of PSFNet.render(train=True) (psfnet.py:605-620, 629-642, 708-713) in one pass.
+// x [N, 2C, H, W] float32 in place: the convolved linear image (left channels first).  randn: standard normal draws of the
+// same shape (torch.randn_like on the device, as the reference draws them); noise_range [N]; weight [N, W] = the
+// reference's torch.linspace(range1, range2, W) ramp, read mirrored for the right channels (torch.flip(weight_l, [-1])).
+__global__ void __launch_bounds__(256)
+gamma_noise_clip_kernel(float *__restrict__ x, const float *__restrict__ randn, const float *__restrict__ noise_range,
+                        const float *__restrict__ weight, int N, int C2, int H, int W) {
+    const int64_t total = (int64_t)N * C2 * H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i % W);
+        const int64_t q = i / ((int64_t)H * W);
+        const int c = (int)(q % C2), n = (int)(q / C2);
+        const float w = weight[(int64_t)n * W + (c < C2 / 2 ? col : W - 1 - col)];
+        const float noise = (randn[i] * noise_range[n]) * w;
+        x[i] = fminf(fmaxf(tone_gamma(x[i]) + noise, 0.0f), 1.0f);
+    }
+}

@@ -80,29 +80,63 @@ class PSFNet(Lensgroup):
         points = torch.stack((x, y, self.z2depth(z)), dim=-1)
         return inp, self.psf(points=points, ks=self.kernel_size, spp=spp)
 
-    def train_psfnet(self, iters=10000, bs=128, lr=1e-4, spp=2048, evaluate_every=1000, result_dir="./results/temp"):
-        """Fit the PSF MLP to ray-traced PSFs generated on the fly (psfnet.py:101-167); no plotting."""
+    fit_graph = True                 # capture forward + loss + backward of the fitting step in a CUDA graph
+
+    def train_psfnet(self, iters=10000, bs=128, lr=1e-4, spp=2048, evaluate_every=1000, result_dir="./results/temp", graph=None):
+        """Fit the PSF MLP to ray-traced PSFs generated on the fly (psfnet.py:101-167); no plotting.
+
+        The targets come from the engine and stay on the device; the loss history is read back once at the end.  With
+        `graph` (default `fit_graph`) the forward, loss and backward of the step are captured once in a CUDA graph and
+        replayed (about 70 kernel launches per iteration become one); GradScaler.step / update and the scheduler run
+        eagerly, as torch's AMP requires."""
         psfnet = self.psfnet
         psfnet.train()
         l2 = nn.MSELoss(reduction="mean")
-        optim = torch.optim.AdamW(psfnet.parameters(), lr)
+        use_graph = self.fit_graph if graph is None else bool(graph)
+        # same AdamW update either way; the fused implementation takes GradScaler's inf check on the device (no host sync)
+        optim = torch.optim.AdamW(psfnet.parameters(), lr, fused=True) if use_graph else torch.optim.AdamW(psfnet.parameters(), lr)
         sche = torch.optim.lr_scheduler.CosineAnnealingLR(optim, T_max=max(int(iters) // 3, 1), eta_min=0)
         scaler = torch.amp.GradScaler("cuda")
-        loss_hist = []
+        ks = self.kernel_size
+        losses = []
+        g = None
+        if use_graph:
+            static_inp = torch.zeros((bs, 3), device=self.device)
+            static_psf = torch.zeros((bs, ks, ks), device=self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                               # warm-up off the capture (no optimizer step: the fit
+                for _ in range(2):                                       # itself starts from the untouched weights)
+                    with torch.autocast(device_type="cuda"):
+                        warm = l2(psfnet(static_inp), static_psf)
+                    scaler.scale(warm).backward()
+                    optim.zero_grad(set_to_none=True)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                with torch.autocast(device_type="cuda"):
+                    static_loss = l2(psfnet(static_inp), static_psf)
+                scaler.scale(static_loss).backward()
         for i in range(iters + 1):
             inp, psf = self.get_training_data(bs=bs, spp=spp)
             inp, psf = inp.to(self.device), psf.to(self.device)
-            with torch.autocast(device_type="cuda"):
-                loss = l2(psfnet(inp), psf)
-            optim.zero_grad()
-            scaler.scale(loss).backward()
+            if g is not None:
+                static_inp.copy_(inp)
+                static_psf.copy_(psf)
+                g.replay()                                               # gradients are rewritten, not accumulated
+                losses.append(static_loss.detach().clone())
+            else:
+                with torch.autocast(device_type="cuda"):
+                    loss = l2(psfnet(inp), psf)
+                optim.zero_grad()
+                scaler.scale(loss).backward()
+                losses.append(loss.detach())
             scaler.step(optim)
             scaler.update()
             sche.step()
-            loss_hist.append(loss.item())
             if (i + 1) % evaluate_every == 0:
                 torch.save(psfnet.state_dict(), f"{result_dir}/iter{i + 1}_PSFNet_{self.model_name}.pkl")
-        return loss_hist
+        return torch.stack(losses).float().cpu().tolist()
 
     # ---- prediction and rendering (psfnet.py:317-336, 589-726) --------------------------------------
     def pred(self, inp):
@@ -183,15 +217,8 @@ class PSFNet(Lensgroup):
         return layers
 
     @torch.no_grad()
-    def render(self, img, depth, foc_dist, train=False):
-        """[N, 6, H, W] dual-pixel image (left RGB, right RGB) from an all-in-focus image [N, 3, H, W] and a depth
-        map [N, 1, H, W] in negative millimetres (psfnet.py:645-714).
-
-        The reference builds the per-pixel PSF tensor [N,H,W,2,ks,ks] of the whole batch (`pred`) and then convolves.
-        Here the image is walked in bands of rows: coordinate grid + first Linear (engine kernel), the 512-wide GEMM chain
-        (cuBLAS, bias + ReLU in the GEMM epilogue), flip / stack / normalise (engine kernel), degamma + gather-convolution +
-        gamma + clip (engine kernel) -- the PSFs of a band stay in the L2 between their producer and their consumer, and
-        memory use does not grow with the image."""
+    def _render_banded(self, img, depth, tone):
+        """degamma (tone & 1) -> per-pixel PSFs -> gather-convolution -> gamma + clip (tone & 2), band by band; [N, 2C, H, W]."""
         if img.dim() != 4:
             raise NotImplementedError("PSFNet.render expects a batched [N, C, H, W] image")
         if not img.is_cuda:
@@ -207,7 +234,6 @@ class PSFNet(Lensgroup):
         rl, rr = torch.empty_like(img32), torch.empty_like(img32)
         rows = max(1, min(int(self.render_band_rows), H))
         nb = max(1, min(N, int(self.render_band_pixels) // (rows * W)))
-        tone = 1 if train else 3
         # Two streams: the GEMM chain of band i + 1 (tensor cores) runs while band i is packed and convolved (memory pipes).
         # raw / psf buffers are double-buffered by hand so that no tensor crosses streams through the caching allocator.
         main = torch.cuda.current_stream(img.device)
@@ -243,12 +269,48 @@ class PSFNet(Lensgroup):
                                             rl[b0:b0 + nbb], rr[b0:b0 + nbb], tone=tone)
                 i += 1
         main.wait_stream(post)
-        render = torch.cat((rl, rr), dim=1)
-        if train:                                                          # noise sits between gamma and clip
-            render = self.gamma(render)
-            render = self.noise(render, img.shape)
-            render = torch.clip(render, 0.0, 1.0)
+        return torch.cat((rl, rr), dim=1)
+
+    @torch.no_grad()
+    def render(self, img, depth, foc_dist, train=False):
+        """[N, 6, H, W] dual-pixel image (left RGB, right RGB) from an all-in-focus image [N, 3, H, W] and a depth
+        map [N, 1, H, W] in negative millimetres (psfnet.py:645-714).
+
+        The reference builds the per-pixel PSF tensor [N,H,W,2,ks,ks] of the whole batch (`pred`) and then convolves.
+        Here the image is walked in bands of rows: coordinate grid + first Linear (engine kernel), the 512-wide GEMM chain
+        (cuBLAS, bias + ReLU in the GEMM epilogue), flip / stack / normalise (engine kernel), degamma + gather-convolution +
+        gamma + clip (engine kernel) -- the PSFs of a band stay in the L2 between their producer and their consumer, and
+        memory use does not grow with the image."""
+        render = self._render_banded(img, depth, 1 if train else 3)
+        if train:                                                          # noise sits between gamma and clip (:708-713)
+            # one draw per call, in the reference's order: noise_range, randn_like, range1, range2 (psfnet.py:629-642)
+            N, W = img.shape[0], img.shape[-1]
+            noise_range = 0.05 * np.random.rand()
+            randn = torch.randn_like(render)
+            range1, range2 = (np.random.rand() / 2), (np.random.rand() / 2 + 0.5)
+            weight = torch.linspace(range1, range2, W).to(img.device).repeat(N, 1)
+            nr_t = torch.full((N,), noise_range, dtype=torch.float32, device=img.device)
+            E.gamma_noise_clip(render, randn, nr_t, weight)
         return render
+
+    @torch.no_grad()
+    def render_focal_stack(self, aif, depth, foc_dists, train=True):
+        """The data-generation loop of 2_dfdp_net.py:161-173 (`for i in range(bs): render(aif[i:i+1], ...)`, then cat) as one
+        banded pass over the whole batch.  Random draws are made per image in the loop's order (noise_range, randn of one
+        image, range1, range2), so a seeded run produces the images the reference's loop would."""
+        N, C, H, W = aif.shape
+        if not train:
+            return self._render_banded(aif, depth, 3)
+        lin = self._render_banded(aif, depth, 1)
+        randn = torch.empty_like(lin)
+        nr, ramps = [], []
+        for i in range(N):
+            nr.append(0.05 * np.random.rand())
+            randn[i:i + 1].normal_()
+            range1, range2 = (np.random.rand() / 2), (np.random.rand() / 2 + 0.5)
+            ramps.append(torch.linspace(range1, range2, W))
+        E.gamma_noise_clip(lin, randn, torch.tensor(nr, dtype=torch.float32).to(aif.device), torch.stack(ramps).to(aif.device))
+        return lin
 
     @torch.no_grad()
     def render_via_pred(self, img, depth, foc_dist, train=False):

@@ -192,6 +192,15 @@ def test_psfnet_fitting_loop(tmp_path, lenses):
         lens.numerics = None
     assert len(hist) == 5 and all(np.isfinite(hist))
     assert (tmp_path / "iter4_PSFNet_mlp.pkl").exists()
+    # the CUDA-graph step (forward + loss + backward captured once) follows the eager step
+    runs = []
+    for use_graph in (False, True):
+        torch.manual_seed(7)
+        np.random.seed(7)
+        fresh = type(lens)(lens_path("rf50mm"), sensor_res=(512, 768), kernel_size=21, device=DEV)
+        fresh.numerics = "adaptive"
+        runs.append(fresh.train_psfnet(iters=5, bs=16, spp=2000, evaluate_every=10 ** 9, result_dir=str(tmp_path), graph=use_graph))
+    np.testing.assert_allclose(runs[0], runs[1], rtol=2e-2)
 
 
 def test_render_banded_vs_reference_half(golden):
@@ -240,3 +249,30 @@ def test_render_banded_large_and_train():
     tr = lens.render(img, depth, foc, train=True)
     assert tr.shape == out.shape and float(tr.min()) >= 0.0 and float(tr.max()) <= 1.0
     assert (tr - out).abs().mean().item() > 1e-4                          # noise was added
+
+
+def test_render_train_tail_and_focal_stack():
+    """render(train=True): the fused gamma + noise + clip kernel against the torch ops of the reference's noise()/gamma()
+    (same seeds, same draw order), and render_focal_stack against the per-image loop of 2_dfdp_net.py:166-171."""
+    from sdirt_b200.deeplens import PSFNet
+    torch.manual_seed(3)
+    lens = PSFNet(lens_path("rf50mm"), sensor_res=(64, 96), kernel_size=11, device=DEV)
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    img = torch.rand((3, 3, 64, 96), device=DEV, generator=gen)
+    depth = -(torch.rand((3, 1, 64, 96), device=DEV, generator=gen) * 5000 + 300)
+    foc = torch.full((3,), -1000.0, device=DEV)
+
+    def seeded(fn):
+        np.random.seed(4)
+        torch.manual_seed(4)
+        return fn()
+    a = seeded(lambda: lens.render(img, depth, foc, train=True))
+    b = seeded(lambda: lens.render_via_pred(img, depth, foc, train=True))
+    assert a.shape == (3, 6, 64, 96) and float(a.min()) >= 0 and float(a.max()) <= 1
+    assert (a - b).abs().max().item() < 2e-3
+    clean = lens.render(img, depth, foc)
+    assert 1e-4 < (a - clean).abs().mean().item() < 0.05                 # sigma <= 0.05 x ramp <= 1
+    stack = seeded(lambda: lens.render_focal_stack(img, depth, foc, train=True))
+    loop = seeded(lambda: torch.cat([lens.render(img[i:i + 1], depth[i:i + 1], foc[i:i + 1], train=True) for i in range(3)], 0))
+    assert (stack - loop).abs().max().item() < 2e-3
+    assert torch.equal(lens.render_focal_stack(img, depth, foc, train=False), clean)

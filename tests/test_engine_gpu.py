@@ -606,3 +606,19 @@ def test_render_rows_equals_whole_image():
         assert torch.equal(bl, rl) and torch.equal(br, rr)
     with pytest.raises(RuntimeError):
         E.render_local_psf_rows(img, psf[:, :4].contiguous(), ks, H - 2, bl, br)
+
+
+def test_gamma_noise_clip_vs_oracle():
+    from sdirt_b200 import _engine as E
+    rng = np.random.default_rng(8)
+    n, c2, h, w = 3, 6, 9, 40
+    x = rng.uniform(0, 300, (n, c2, h, w)).astype(np.float32)              # linear image values (degamma range)
+    rn = rng.normal(0, 1, x.shape).astype(np.float32)
+    nr = (0.05 * rng.random(n)).astype(np.float32)
+    wt = np.stack([O._torch_linspace(a, b, w) for a, b in zip(rng.random(n) / 2, rng.random(n) / 2 + 0.5)])
+    got = E.gamma_noise_clip(cu(x), cu(rn), cu(nr), cu(wt)).cpu().numpy()
+    want = O.gamma_noise_clip(x, rn, nr, wt)
+    np.testing.assert_allclose(got, want, atol=2e-6)
+    assert got.min() >= 0 and got.max() <= 1 and (got > 0).mean() > 0.5
+    with pytest.raises(RuntimeError):
+        E.gamma_noise_clip(cu(x), cu(rn), cu(nr), cu(wt[:, :-1]))

@@ -23,6 +23,20 @@ def main():
         dt = (time.perf_counter() - t0) / n
         print(f"numerics={numerics}: get_training_data(bs=64, spp=20000): {dt * 1e3:.3f} ms / call = {64 * 20000 / dt:.3e} rays/s, "
               f"{64 / dt:.0f} PSFs/s")
+    # whole fitting iterations (1_fit_psfnet.py / psfnet.py:101-167): ray-traced targets + MLP forward/backward/AdamW step
+    import tempfile
+    lens.numerics = "adaptive"
+    with tempfile.TemporaryDirectory() as tmp:
+        for use_graph in (False, True):
+            lens.train_psfnet(iters=5, bs=64, spp=20000, evaluate_every=10 ** 9, result_dir=tmp, graph=use_graph)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_it = 200
+            lens.train_psfnet(iters=n_it - 1, bs=64, spp=20000, evaluate_every=10 ** 9, result_dir=tmp, graph=use_graph)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_it
+            print(f"train_psfnet(bs=64, spp=20000, graph={use_graph}): {dt * 1e3:.3f} ms / iteration = {1 / dt:.0f} it/s "
+                  f"(the reference's 90 k-iteration fit: {90000 * dt / 60:.1f} min)")
     pr = cProfile.Profile()
     pr.enable()
     for _ in range(20):
