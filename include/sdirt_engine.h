@@ -25,6 +25,7 @@
  *                                      PSFNet.degamma / gamma / clip       deeplens/psfnet.py:589-620,706-713
  *   sdirt_mlp_input_layer           <- coordinate grid + first Linear+ReLU deeplens/psfnet.py:681-694; psfnet_arch.py:40-41
  *   sdirt_psf_pack                  <- PSFNet.pred: flip, stack, normalise deeplens/psfnet.py:326-333
+ *   sdirt_mlp_fused_pred            <- PSFNet.pred (grid, MLP x2, flip, stack, normalise) deeplens/psfnet.py:317-336, 681-705; psfnet_arch.py:32-56
  *   sdirt_gamma_noise_clip          <- PSFNet.gamma / noise / clip (train) deeplens/psfnet.py:605-620, 629-642, 708-713
  *
  * Conventions: every pointer marked "dev" is device memory owned by the caller (a torch CUDA tensor's
@@ -225,6 +226,30 @@ int sdirt_mlp_input_layer(const float *xs_dev, const float *ys_dev, const float 
                           int b0, int nb, int row0, int n_rows, const void *w1_half_dev, const void *b1_half_dev,
                           int n1, void *out_half_dev, void *stream);
 int sdirt_psf_pack(const void *raw_half_dev, int64_t n_pixels, int ld, int ks, void *psf_half_dev, void *stream);
+
+/* ---- PSFNet.pred for a window of pixels as ONE tensor-core kernel (csrc/mlp_fused.cuh) -------------------------------
+ * Replaces, for the pixels of images [b0, b0 + nb), rows [row0, row0 + n_rows): the coordinate grid, both MLP
+ * evaluations under CUDA autocast (psfnet_arch.py:32-56), flip / stack / normalise (psfnet.py:317-336) -- i.e.
+ * sdirt_mlp_input_layer + the cuBLAS GEMM chain + sdirt_psf_pack -- and writes psf_half_dev[n_pixels, 2, ks, ks].
+ * The MLP is described by its shape: a first Linear(3 -> n1) + ReLU, then n_layers Linear(K[l] -> N[l]) + ReLU whose
+ * weights are handed over once through sdirt_mlp_fused_pack_layer (tcgen05 operand tiles, SWIZZLE_128B) into caller-owned
+ * buffers of sdirt_mlp_fused_layout's sizes.  Hidden widths: multiples of 64 up to 512; N[last] = ks*ks; ks in {7, 11, 21};
+ * the window must hold a multiple of 4 pixels. */
+#define SDIRT_MLP_MAX_LAYERS 12
+typedef struct sdirt_mlp_shape {
+    int32_t n_layers;                     /* tensor-core layers, i.e. every Linear after the first */
+    int32_t n1;                           /* width of the first Linear (64 or 128) */
+    int32_t K[SDIRT_MLP_MAX_LAYERS];      /* input width of each layer (K[0] = n1, K[l] = N[l-1]) */
+    int32_t N[SDIRT_MLP_MAX_LAYERS];      /* output width of each layer (true, unpadded) */
+} sdirt_mlp_shape;
+/* Returns the bytes of the packed-weight buffer (or -1); fills per-layer offsets and the float count of the bias buffer. */
+int64_t sdirt_mlp_fused_layout(const sdirt_mlp_shape *shape, int64_t *w_off_out, int32_t *b_off_out, int64_t *bias_floats_out);
+int sdirt_mlp_fused_pack_layer(const sdirt_mlp_shape *shape, int layer, const void *w_half_dev /*[N,K]*/,
+                               const void *b_half_dev /*[N]*/, void *packed_w_dev, float *packed_bias_dev, void *stream);
+int sdirt_mlp_fused_pred(const sdirt_mlp_shape *shape, const void *packed_w_dev, const float *packed_bias_dev,
+                         const void *w1_half_dev /*[n1,3]*/, const void *b1_half_dev /*[n1]*/,
+                         const float *xs_dev, const float *ys_dev, const float *z_dev, int B, int H, int W,
+                         int b0, int nb, int row0, int n_rows, int ks, void *psf_half_dev, void *stream);
 
 /* gamma -> sensor noise -> clip(0,1), the tail of PSFNet.render(train=True) (psfnet.py:605-620, 629-642, 708-713), in
  * place on x_dev[N, 2C, H, W] (the convolved linear image, left channels first).  randn_dev: standard-normal draws of

@@ -26,6 +26,13 @@ NUMERICS_STRICT, NUMERICS_FAST, NUMERICS_HYBRID, NUMERICS_ADAPTIVE = 0, 1, 2, 3
 DEFAULT_NUMERICS = NUMERICS_STRICT
 
 
+MLP_MAX_LAYERS = 12
+
+
+class MlpShape(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("n1", C.c_int32), ("K", C.c_int32 * MLP_MAX_LAYERS), ("N", C.c_int32 * MLP_MAX_LAYERS)]
+
+
 class DPParams(C.Structure):
     _fields_ = [("h", C.c_float), ("f", C.c_float), ("w", C.c_float), ("r", C.c_float)]
 
@@ -70,6 +77,10 @@ def lib():
     L.sdirt_render_local_psf_rows.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
     L.sdirt_mlp_input_layer.argtypes = [vp, vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, cint, vp, vp]
     L.sdirt_psf_pack.argtypes = [vp, i64, cint, cint, vp, vp]
+    L.sdirt_mlp_fused_layout.argtypes = [C.POINTER(MlpShape), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(i64)]
+    L.sdirt_mlp_fused_layout.restype = i64
+    L.sdirt_mlp_fused_pack_layer.argtypes = [C.POINTER(MlpShape), cint, vp, vp, vp, vp, vp]
+    L.sdirt_mlp_fused_pred.argtypes = [C.POINTER(MlpShape), vp, vp, vp, vp, vp, vp, vp, cint, cint, cint, cint, cint, cint, cint, cint, vp, vp]
     L.sdirt_gamma_noise_clip.argtypes = [vp, vp, vp, vp, cint, cint, cint, cint, vp]
     L.sdirt_fp32_peak_probe.argtypes = [vp, cint, cint, cint, vp]
     _lib = L
@@ -345,6 +356,54 @@ def psf_pack(raw, ks, out=None):
     _check(lib().sdirt_psf_pack(_dev(raw, "raw", torch.float16), rows // 2, int(ld), int(ks), _dev(out, "out", torch.float16),
                                 _stream(raw)))
     return out
+
+
+class FusedMlp:
+    """The PSF MLP handed over to the fused tensor-core kernel (sdirt_mlp_fused_pred): first Linear (w1 [n1,3], b1 [n1]) kept
+    as is, every later Linear packed once into tcgen05 operand tiles.  `linears`: list of (weight [N,K], bias [N]) CUDA
+    tensors in layer order, the first one being the 3 -> n1 layer."""
+
+    def __init__(self, linears):
+        (w1, b1), rest = linears[0], linears[1:]
+        if w1.shape[1] != 3 or not rest:
+            raise RuntimeError("sdirt_engine: FusedMlp expects Linear(3 -> n1) followed by at least one more Linear")
+        dev = w1.device
+        sh = MlpShape()
+        sh.n_layers, sh.n1 = len(rest), w1.shape[0]
+        if sh.n_layers > MLP_MAX_LAYERS:
+            raise RuntimeError(f"sdirt_engine: at most {MLP_MAX_LAYERS} layers after the first")
+        for l, (w, _) in enumerate(rest):
+            sh.N[l], sh.K[l] = w.shape
+        bias_floats = C.c_int64(0)
+        nbytes = lib().sdirt_mlp_fused_layout(C.byref(sh), None, None, C.byref(bias_floats))
+        if nbytes < 0:
+            raise RuntimeError("sdirt_engine: " + lib().sdirt_last_error().decode())
+        self.shape = sh
+        self.w1 = w1.detach().half().contiguous()
+        self.b1 = b1.detach().half().contiguous()
+        self.packed_w = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.packed_b = torch.empty(bias_floats.value, dtype=torch.float32, device=dev)
+        for l, (w, b) in enumerate(rest):
+            w16, b16 = w.detach().half().contiguous(), b.detach().half().contiguous()
+            _check(lib().sdirt_mlp_fused_pack_layer(C.byref(sh), l, _dev(w16, "w", torch.float16), _dev(b16, "b", torch.float16),
+                                                    C.c_void_p(self.packed_w.data_ptr()), _dev(self.packed_b, "bias"), _stream(w16)))
+        self.n_out = int(sh.N[sh.n_layers - 1])
+
+    def pred(self, xs, ys, z, b0, nb, row0, n_rows, ks, out=None):
+        """Normalised L/R kernels [P,2,ks,ks] float16 of the pixels of images [b0, b0+nb), rows [row0, row0+n_rows)."""
+        bsz, h, w = z.shape
+        px = nb * n_rows * w
+        if out is None:
+            out = torch.empty((px, 2, ks, ks), device=z.device, dtype=torch.float16)
+        elif out.numel() != px * 2 * ks * ks:
+            raise RuntimeError("sdirt_engine: `out` must hold [P,2,ks,ks]")
+        if xs.numel() != w or ys.numel() != h:
+            raise RuntimeError("sdirt_engine: xs / ys do not match z")
+        _check(lib().sdirt_mlp_fused_pred(C.byref(self.shape), C.c_void_p(self.packed_w.data_ptr()), _dev(self.packed_b, "bias"),
+                                          _dev(self.w1, "w1", torch.float16), _dev(self.b1, "b1", torch.float16), _dev(xs, "xs"),
+                                          _dev(ys, "ys"), _dev(z, "z"), bsz, h, w, int(b0), int(nb), int(row0), int(n_rows), int(ks),
+                                          _dev(out, "out", torch.float16), _stream(z)))
+        return out
 
 
 def gamma_noise_clip(x, randn, noise_range, weight):

@@ -188,6 +188,16 @@ class PSFNet(Lensgroup):
     render_band_rows = 16            # rows per band (the render kernels' tile height)
     render_band_pixels = 98304       # pixels per band batch: images are grouped until a band holds about this many
     render_overlap = True            # pack + convolve band i on a second stream while the GEMMs of band i + 1 run
+    mlp_engine = "cublas"            # "fused": the whole of `pred` for a band as one tcgen05 kernel (csrc/mlp_fused.cuh)
+
+    def _mlp_fused(self):
+        """The MLP packed for sdirt_mlp_fused_pred, cached on the parameters' versions."""
+        lin = [m for m in self.psfnet.net if isinstance(m, nn.Linear)]
+        key = tuple((m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(), m.bias._version) for m in lin)
+        cache = getattr(self, "_mlp_fused_cache", None)
+        if cache is None or cache[0] != key:
+            cache = self._mlp_fused_cache = (key, E.FusedMlp([(m.weight, m.bias) for m in lin]))
+        return cache[1]
 
     def _render_post_stream(self, device):
         st = getattr(self, "_post_stream", None)
@@ -240,10 +250,11 @@ class PSFNet(Lensgroup):
         post = self._render_post_stream(img.device) if self.render_overlap else main
         n_out = chain[-1][0].shape[1]
         max_px = nb * rows * W
-        raw = [torch.empty((2 * max_px, n_out), device=img.device, dtype=torch.float16) for _ in range(2)]
+        fused = self._mlp_fused() if (self.mlp_engine == "fused" and max_px % 4 == 0 and (rows * W) % 4 == 0) else None
+        raw = [torch.empty((2 * max_px, n_out), device=img.device, dtype=torch.float16) for _ in range(2)] if fused is None else None
         psf = [torch.empty((max_px, 2, ks, ks), device=img.device, dtype=torch.float16) for _ in range(2)]
-        raw_ready = [torch.cuda.Event() for _ in range(2)]
-        raw_free = [None, None]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        buf_free = [None, None]
         post.wait_stream(main)                                             # img32 / z / outputs are ready for the post stream
         i = 0
         for b0 in range(0, N, nb):
@@ -252,21 +263,31 @@ class PSFNet(Lensgroup):
                 nr = min(rows, H - y0)
                 px = nbb * nr * W
                 k = i & 1
-                h = E.mlp_input_layer(xs, ys, z, b0, nbb, y0, nr, w1, b1)
-                for wt, b in chain[:-1]:
-                    h = torch._addmm_activation(b, h, wt)                 # relu(h @ W^T + b), fp16 in / fp32 accumulate / fp16 out
-                if raw_free[k] is not None:
-                    main.wait_event(raw_free[k])                          # band i - 2 has been packed out of this buffer
-                torch._addmm_activation(chain[-1][1], h, chain[-1][0], out=raw[k][:2 * px])
-                raw_ready[k].record(main)
+                if fused is not None and px % 4 == 0:
+                    if buf_free[k] is not None:
+                        main.wait_event(buf_free[k])                      # band i - 2 has been convolved out of this buffer
+                    fused.pred(xs, ys, z, b0, nbb, y0, nr, ks, out=psf[k][:px])
+                    packed = True
+                else:
+                    if raw is None:
+                        raw = [torch.empty((2 * max_px, n_out), device=img.device, dtype=torch.float16) for _ in range(2)]
+                    h = E.mlp_input_layer(xs, ys, z, b0, nbb, y0, nr, w1, b1)
+                    for wt, b in chain[:-1]:
+                        h = torch._addmm_activation(b, h, wt)             # relu(h @ W^T + b), fp16 in / fp32 accumulate / fp16 out
+                    if buf_free[k] is not None:
+                        main.wait_event(buf_free[k])
+                    torch._addmm_activation(chain[-1][1], h, chain[-1][0], out=raw[k][:2 * px])
+                    packed = False
+                ready[k].record(main)
                 with torch.cuda.stream(post):
-                    post.wait_event(raw_ready[k])
-                    E.psf_pack(raw[k][:2 * px], ks, out=psf[k][:px])
-                    if post is not main:
-                        raw_free[k] = torch.cuda.Event()
-                        raw_free[k].record(post)
+                    post.wait_event(ready[k])
+                    if not packed:
+                        E.psf_pack(raw[k][:2 * px], ks, out=psf[k][:px])
                     E.render_local_psf_rows(img32[b0:b0 + nbb], psf[k][:px].view(nbb, nr, W, 2, ks, ks), ks, y0,
                                             rl[b0:b0 + nbb], rr[b0:b0 + nbb], tone=tone)
+                    if post is not main:
+                        buf_free[k] = torch.cuda.Event()
+                        buf_free[k].record(post)
                 i += 1
         main.wait_stream(post)
         return torch.cat((rl, rr), dim=1)

@@ -276,3 +276,20 @@ def test_render_train_tail_and_focal_stack():
     loop = seeded(lambda: torch.cat([lens.render(img[i:i + 1], depth[i:i + 1], foc[i:i + 1], train=True) for i in range(3)], 0))
     assert (stack - loop).abs().max().item() < 2e-3
     assert torch.equal(lens.render_focal_stack(img, depth, foc, train=False), clean)
+
+
+def test_render_fused_mlp_engine(golden):
+    """PSFNet.render with mlp_engine = "fused" (pred as one tcgen05 kernel per band) against the reference's fp16 golden and
+    against the cuBLAS route."""
+    from sdirt_b200.deeplens import PSFNet
+    g = golden("predhalf")
+    torch.manual_seed(5)
+    lens = PSFNet(lens_path("rf50mm"), sensor_res=(16, 24), kernel_size=21, device=DEV)
+    img, depth, foc = (torch.from_numpy(g[k]).to(DEV) for k in ("img", "depth", "foc"))
+    base = lens.render(img, depth, foc)
+    lens.mlp_engine = "fused"
+    out = lens.render(img, depth, foc)
+    assert np.abs(out.cpu().numpy() - g["render_out"]).max() < 2e-3
+    assert (out - base).abs().max().item() < 1e-3
+    lens.render_band_rows, lens.render_band_pixels = 8, 1                   # several bands, one image at a time
+    assert torch.equal(lens.render(img, depth, foc), out)

@@ -622,3 +622,72 @@ def test_gamma_noise_clip_vs_oracle():
     assert got.min() >= 0 and got.max() <= 1 and (got > 0).mean() > 0.5
     with pytest.raises(RuntimeError):
         E.gamma_noise_clip(cu(x), cu(rn), cu(nr), cu(wt[:, :-1]))
+
+
+# ---- PSFNet.pred as one tcgen05 kernel (csrc/mlp_fused.cuh) --------------------------------------------------------------
+def _seeded_linears(ks=21, seed=5):
+    from test_oracle_golden import seeded_mlp_weights
+    return [(torch.from_numpy(w).to(DEV), torch.from_numpy(b).to(DEV)) for w, b in seeded_mlp_weights(seed, ks)]
+
+
+def test_mlp_fused_pred_vs_reference_and_oracle(golden):
+    """The fused tensor-core kernel against (1) the reference's own pred() run with its MLP in fp16 (predhalf.npz), (2) the
+    oracle's restatement, (3) the cuBLAS route of the engine (same rounding points: expected equal up to GEMM summation order)."""
+    from sdirt_b200 import _engine as E
+    from test_oracle_golden import half_ulps, seeded_mlp_weights
+    g = golden("predhalf")
+    lin = _seeded_linears()
+    fused = E.FusedMlp(lin)
+    xs, ys = cu(O._torch_linspace(-1, 1, 24)), cu(O._torch_linspace(1, -1, 16))
+    z = cu(g["z"])
+    got = fused.pred(xs, ys, z, 0, 2, 0, 16, 21).float().cpu().numpy().reshape(2, 16, 24, 2, 21, 21)
+    ref = g["psf"].astype(np.float32)
+    ok = np.isfinite(ref).all((-1, -2))
+    scale = ref[ok].max()
+    assert np.abs(got[ok] - ref[ok]).max() <= 4e-3 * scale and np.abs(got[ok] - ref[ok]).mean() <= 2e-4 * scale
+    assert (got[~ok] == 0).all()
+    # a window of one image: rows 5..12 of image 1, against the oracle on the same rows
+    sub = fused.pred(xs, ys, z, 1, 1, 5, 8, 21).float().cpu().numpy()
+    rows = O.mlp_input_rows(O._torch_linspace(-1, 1, 24), O._torch_linspace(1, -1, 16), g["z"], 1, 1, 5, 8)
+    want = O.psf_pack_half(O.mlp_forward_half(seeded_mlp_weights(), rows), 21)
+    assert np.abs(sub - want).max() <= 4e-3 * scale
+    np.testing.assert_array_equal(sub, got[1, 5:13].reshape(sub.shape))       # tiling does not change a pixel's result
+    # the engine's cuBLAS route
+    w1, b1 = lin[0][0].half().contiguous(), lin[0][1].half().contiguous()
+    h = E.mlp_input_layer(xs, ys, z, 0, 2, 0, 16, w1, b1)
+    for i, (w, b) in enumerate(lin[1:]):
+        w16, b16 = w.half(), b.half()
+        if i == len(lin) - 2:
+            w16, b16 = torch.cat((w16, w16.new_zeros(7, w16.shape[1]))), torch.cat((b16, b16.new_zeros(7)))
+        h = torch._addmm_activation(b16.contiguous(), h, w16.contiguous().t())
+    via = E.psf_pack(h, 21).float().cpu().numpy().reshape(got.shape)
+    u = half_ulps(got, via)
+    assert u.max() <= 2 and (u == 0).mean() > 0.99
+
+
+def test_mlp_fused_other_windows_and_errors():
+    from sdirt_b200 import _engine as E
+    for ks in (7, 11):
+        lin = _seeded_linears(ks=ks, seed=9)
+        fused = E.FusedMlp(lin)
+        gen = torch.Generator(device=DEV).manual_seed(ks)
+        z = torch.rand((3, 20, 36), device=DEV, generator=gen)                # 3 x 20 x 36 pixels: a ragged last tile
+        xs, ys = cu(O._torch_linspace(-1, 1, 36)), cu(O._torch_linspace(1, -1, 20))
+        got = fused.pred(xs, ys, z, 0, 3, 0, 20, ks)
+        w1, b1 = lin[0][0].half().contiguous(), lin[0][1].half().contiguous()
+        h = E.mlp_input_layer(xs, ys, z, 0, 3, 0, 20, w1, b1)
+        for i, (w, b) in enumerate(lin[1:]):
+            w16, b16 = w.half(), b.half()
+            padn = (-w16.shape[0]) % 8
+            if padn:
+                w16, b16 = torch.cat((w16, w16.new_zeros(padn, w16.shape[1]))), torch.cat((b16, b16.new_zeros(padn)))
+            h = torch._addmm_activation(b16.contiguous(), h, w16.contiguous().t())
+        via = E.psf_pack(h, ks)
+        assert got.shape == via.shape == (3 * 20 * 36, 2, ks, ks)
+        assert (got.float() - via.float()).abs().max().item() <= 4e-3 * via.float().max().item()
+        assert float((got == via).float().mean()) > 0.99
+    with pytest.raises(RuntimeError):
+        fused.pred(xs, ys, z[:, :, :35].contiguous(), 0, 1, 0, 1, 11)          # 35 pixels: not a multiple of 4
+    with pytest.raises(RuntimeError):
+        E.FusedMlp([(torch.zeros(128, 3, device=DEV), torch.zeros(128, device=DEV)), (torch.zeros(100, 128, device=DEV), torch.zeros(100, device=DEV)),
+                    (torch.zeros(49, 100, device=DEV), torch.zeros(49, device=DEV))])     # hidden width 100: not a multiple of 64

@@ -1,0 +1,60 @@
+"""Scratch check of the fused tcgen05 PSF-MLP kernel against the cuBLAS route (input layer kernel + GEMM chain + pack).
+Usage: fused_debug.py [H W B]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from sdirt_b200 import _engine as E, lens_file
+from sdirt_b200.deeplens import PSFNet
+
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    a = [int(v) for v in sys.argv[1:]]
+    H, W, B = (a + [16, 24, 2])[:3] if len(a) < 3 else a[:3]
+    ks = 21
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    lens = PSFNet(lens_file("rf50mm"), sensor_res=(H, W), kernel_size=ks, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    z = torch.rand((B, H, W), device=dev, generator=g)
+    xs, ys = torch.linspace(-1, 1, W).to(dev), torch.linspace(1, -1, H).to(dev)
+    (w1, b1), chain = lens._mlp_half_layers()
+    rows = min(16, H)
+
+    def cublas():
+        h = E.mlp_input_layer(xs, ys, z, 0, B, 0, rows, w1, b1)
+        for wt, b in chain:
+            h = torch._addmm_activation(b, h, wt)
+        return E.psf_pack(h, ks)
+    want = cublas()
+    fused = lens._mlp_fused()
+    torch.cuda.synchronize()
+    print("packed weights", fused.packed_w.numel(), "bytes; launching fused kernel", flush=True)
+    got = fused.pred(xs, ys, z, 0, B, 0, rows, ks)
+    torch.cuda.synchronize()
+    d = (got.float() - want.float()).abs()
+    scale = want.float().abs().max().item()
+    print(f"P={B * rows * W} px: max |fused - cublas| = {d.max().item():.3e} (max value {scale:.3e}), mean {d.mean().item():.3e}, "
+          f"exact {float((got == want).float().mean()):.4f}, nan {int(torch.isnan(got.float()).sum())}")
+    bad = (d > 2e-2 * scale).nonzero()
+    if len(bad):
+        print("first mismatches (pixel, side, u, v):", bad[:8].tolist())
+        p0 = bad[0][0].item()
+        print("got ", got[p0, 0, 0, :8].tolist()); print("want", want[p0, 0, 0, :8].tolist())
+    px = B * rows * W
+    flop = px * 2 * 2 * (3 * 128 + 128 * 512 + 8 * 512 * 512 + 512 * 441)
+    t_f = timed(lambda: fused.pred(xs, ys, z, 0, B, 0, rows, ks))
+    t_c = timed(cublas)
+    print(f"fused {t_f * 1e3:.0f} us = {flop / t_f / 1e9:.0f} TFLOP/s; cuBLAS route {t_c * 1e3:.0f} us = {flop / t_c / 1e9:.0f} TFLOP/s")
+
+
+main()
