@@ -251,6 +251,10 @@ int sdirt_mlp_fused_pred(const sdirt_mlp_shape *shape, const void *packed_w_dev,
                          const float *xs_dev, const float *ys_dev, const float *z_dev, int B, int H, int W,
                          int b0, int nb, int row0, int n_rows, int ks, void *psf_half_dev, void *stream);
 
+/* Measurement helper: a device buffer [grid][8] of int64 that the next sdirt_mlp_fused_pred launches fill with cycle counters
+ * (MMA loop, its waits for weights / for the epilogue; epilogue loop, its waits); NULL switches it off. */
+void sdirt_mlp_fused_debug(long long *counters_dev);
+
 /* gamma -> sensor noise -> clip(0,1), the tail of PSFNet.render(train=True) (psfnet.py:605-620, 629-642, 708-713), in
  * place on x_dev[N, 2C, H, W] (the convolved linear image, left channels first).  randn_dev: standard-normal draws of
  * that shape; noise_range_dev[N]; weight_dev[N, W]: the linspace(range1, range2, W) ramp, read mirrored for the right

@@ -35,8 +35,9 @@ constexpr int MAX_N1 = 128;
 constexpr int OFF_W = A_BYTES;
 constexpr int OFF_W1 = OFF_W + STAGES * STAGE_BYTES;
 constexpr int OFF_BAR = OFF_W1 + MAX_N1 * 16;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
-constexpr int THREADS = 192;
+constexpr int SMEM_BYTES = OFF_BAR + 128;                // barriers, TMEM slot
+constexpr int EPI_THREADS = 256, PROD_WARP = 8, MMA_WARP = 9;
+constexpr int THREADS = 320;
 static_assert(SMEM_BYTES <= 227 * 1024, "fused MLP tile does not fit in shared memory");
 
 struct Net {
@@ -66,21 +67,61 @@ __device__ __forceinline__ unsigned long long smem_desc(unsigned addr) {
 // kind::f16: D = f32, A = B = f16, both K-major, M = 128
 __device__ __forceinline__ unsigned instr_desc(int n) { return (1u << 4) | ((unsigned)(n >> 3) << 17) | ((unsigned)(TM >> 4) << 24); }
 
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-    unsigned r[32];
+// 32 consecutive fp32 columns of this thread's TMEM lane: the load is asynchronous, the registers may be read only after
+// tmem_wait32 (which names them as operands so that the compiler keeps every use behind the wait).
+#define TM_R(i) "=r"(r[i])
+#define TM_RW(i) "+r"(r[i])
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        "tcgen05.wait::ld.sync.aligned;\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : TM_R(0), TM_R(1), TM_R(2), TM_R(3), TM_R(4), TM_R(5), TM_R(6), TM_R(7), TM_R(8), TM_R(9), TM_R(10), TM_R(11), TM_R(12),
+          TM_R(13), TM_R(14), TM_R(15), TM_R(16), TM_R(17), TM_R(18), TM_R(19), TM_R(20), TM_R(21), TM_R(22), TM_R(23), TM_R(24),
+          TM_R(25), TM_R(26), TM_R(27), TM_R(28), TM_R(29), TM_R(30), TM_R(31)
         : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait32(unsigned (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+        : TM_RW(0), TM_RW(1), TM_RW(2), TM_RW(3), TM_RW(4), TM_RW(5), TM_RW(6), TM_RW(7), TM_RW(8), TM_RW(9), TM_RW(10), TM_RW(11),
+          TM_RW(12), TM_RW(13), TM_RW(14), TM_RW(15), TM_RW(16), TM_RW(17), TM_RW(18), TM_RW(19), TM_RW(20), TM_RW(21), TM_RW(22),
+          TM_RW(23), TM_RW(24), TM_RW(25), TM_RW(26), TM_RW(27), TM_RW(28), TM_RW(29), TM_RW(30), TM_RW(31)
+        :: "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(unsigned taddr, unsigned (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : TM_R(0), TM_R(1), TM_R(2), TM_R(3), TM_R(4), TM_R(5), TM_R(6), TM_R(7), TM_R(8), TM_R(9), TM_R(10), TM_R(11), TM_R(12),
+          TM_R(13), TM_R(14), TM_R(15)
+        : "r"(taddr) : "memory");
+}
+// The same load, ordered after every use of `dep` that precedes it and before every use that follows it in program order:
+// naming `dep` as in/out operands keeps the compiler from sinking the issue below the arithmetic on `dep`, which would
+// serialise "load, wait, compute" again.
+__device__ __forceinline__ void tmem_ld16_issue_after(unsigned taddr, unsigned (&r)[16], unsigned (&dep)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n"
+        : TM_R(0), TM_R(1), TM_R(2), TM_R(3), TM_R(4), TM_R(5), TM_R(6), TM_R(7), TM_R(8), TM_R(9), TM_R(10), TM_R(11), TM_R(12),
+          TM_R(13), TM_R(14), TM_R(15),
+          "+r"(dep[0]), "+r"(dep[1]), "+r"(dep[2]), "+r"(dep[3]), "+r"(dep[4]), "+r"(dep[5]), "+r"(dep[6]), "+r"(dep[7]),
+          "+r"(dep[8]), "+r"(dep[9]), "+r"(dep[10]), "+r"(dep[11]), "+r"(dep[12]), "+r"(dep[13]), "+r"(dep[14]), "+r"(dep[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait16(unsigned (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+        : TM_RW(0), TM_RW(1), TM_RW(2), TM_RW(3), TM_RW(4), TM_RW(5), TM_RW(6), TM_RW(7), TM_RW(8), TM_RW(9), TM_RW(10), TM_RW(11),
+          TM_RW(12), TM_RW(13), TM_RW(14), TM_RW(15)
+        :: "memory");
+}
+#undef TM_R
+#undef TM_RW
+
+// 16-byte read-only load that stays where it is written (a plain __ldg may be hoisted across the asm statements around it; in
+// the fully unrolled last layer that piles hundreds of registers up)
+__device__ __forceinline__ float4 ldg_f4_here(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 
 // byte offset of the 16-byte chunk holding columns [col, col + 8) of row `row` in the swizzled activation tile
@@ -95,20 +136,102 @@ __device__ __forceinline__ unsigned pack_relu_h2(float a, float b) {
 }
 __device__ __forceinline__ float relu_h(float a) { return __half2float(__float2half_rn(fmaxf(a, 0.0f))); }
 
+// 32 accumulator columns + bias -> ReLU -> fp16, packed two per register
+__device__ __forceinline__ void bias_relu_pack(const unsigned (&r)[32], const float4 (&bv)[8], unsigned (&o)[16]) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        o[2 * g] = pack_relu_h2(__uint_as_float(r[4 * g]) + bv[g].x, __uint_as_float(r[4 * g + 1]) + bv[g].y);
+        o[2 * g + 1] = pack_relu_h2(__uint_as_float(r[4 * g + 2]) + bv[g].z, __uint_as_float(r[4 * g + 3]) + bv[g].w);
+    }
+}
+__device__ __forceinline__ void store_a_chunks(unsigned char *sA, int row, int col, const unsigned (&o)[16]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4 *>(sA + a_chunk_off(row, col + 8 * g)) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+}
+
+// Last layer, one 16-column piece of the accumulator: relu(acc + bias) rounded to fp16 (two values per F2FP / HMNMX2).
+// PASS 0 adds it to the kernel-row sums, PASS 1 (the accumulator is read a second time: TMEM loads are cheap, a hundred
+// live registers are not) divides and stages the result at its final position.  The next piece is in flight while this one
+// is used.  GRP: which half of the columns (split at SPLIT) this warp owns; RIGHT: the warp's rows are right kernels (rows
+// 64..127 of a tile), whose columns are flipped inside every kernel row -- both compile-time, so every staged address is
+// an immediate.
+struct TailState {
+    float part, rs, rs_x, den, rc;      // total of finished kernel rows, running row, the straddling row's piece; denominator
+    __half *dst;                        // this row of the staged block
+    const float *bl;                    // last layer's bias
+    unsigned lane_addr;
+    int c_lo;
+};
+template <int KS, int PASS, int GRP, int RIGHT>
+__device__ __forceinline__ void tail_piece(const int hcx, unsigned (&cur)[16], unsigned (&nxt)[16], TailState &st) {
+    constexpr int KK = KS * KS, KC = (KK + 31) / 32, HC = (KC + 1) / 2, SPLIT = 32 * HC;
+    constexpr int U_X = (SPLIT < KK) ? SPLIT / KS : -1;
+    constexpr bool STRADDLE = U_X >= 0 && (SPLIT % KS) != 0;
+    float4 bv[4];                                             // this piece's biases (the padded bias row covers every chunk)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bv[g] = ldg_f4_here(reinterpret_cast<const float4 *>(st.bl + st.c_lo + 16 * hcx) + g);
+    tmem_wait16(cur);
+    if (hcx + 1 < 2 * HC) tmem_ld16_issue_after(st.lane_addr + (unsigned)(st.c_lo + 16 * (hcx + 1)), nxt, cur);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        const int col = (GRP ? SPLIT : 0) + 16 * hcx + i;     // a compile-time constant once hcx is unrolled
+        const bool live0 = GRP ? (col < KK) : (col < KK && col < SPLIT);
+        const bool live1 = GRP ? (col + 1 < KK) : (col + 1 < KK && col + 1 < SPLIT);
+        if (!live0) continue;
+        const float b0 = (i & 2) ? bv[i >> 2].z : bv[i >> 2].x, b1 = (i & 2) ? bv[i >> 2].w : bv[i >> 2].y;
+        // relu(round_fp16(acc + bias)) for two columns at once
+        const __half2 h = __hmax2(__floats2half2_rn(__uint_as_float(cur[i]) + b0, __uint_as_float(cur[i + 1]) + b1), __float2half2_rn(0.0f));
+        const float v0 = __low2float(h), v1 = live1 ? __high2float(h) : 0.0f;
+        if (PASS == 0) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k == 1 && !live1) break;
+                const int c = col + k;
+                st.rs += k ? v1 : v0;
+                // end of a kernel row (or of this thread's piece of the straddling row)
+                if (((c + 1) % KS == 0) || (!GRP && c + 1 == SPLIT) || (c + 1 == KK)) {
+                    if (STRADDLE && c / KS == U_X) st.rs_x = st.rs;
+                    else st.part += __half2float(__float2half_rn(st.rs));
+                    st.rs = 0.0f;
+                }
+            }
+        } else {
+            // IEEE v / den from the refined reciprocal (div_rn's sequence); den = rc = 0 for an all-zero kernel -> 0
+            const float q0 = v0 * st.rc, q1 = v1 * st.rc;
+            const float r0 = fmaf(st.rc, fmaf(-st.den, q0, v0), q0), r1 = fmaf(st.rc, fmaf(-st.den, q1, v1), q1);
+            const int u0 = col / KS, w0 = col - u0 * KS, u1 = (col + 1) / KS, w1 = (col + 1) - u1 * KS;
+            const int p0 = RIGHT ? u0 * KS + (KS - 1 - w0) : col, p1 = RIGHT ? u1 * KS + (KS - 1 - w1) : col + 1;
+            if (!RIGHT && live1 && (col & 1) == 0) {          // left rows start 4-byte aligned: one 32-bit store per pair
+                const __half2 o = __floats2half2_rn(r0, r1);
+                *reinterpret_cast<__half2 *>(st.dst + col) = o;
+            } else {
+                st.dst[p0] = __float2half_rn(r0);
+                if (live1) st.dst[p1] = __float2half_rn(r1);
+            }
+        }
+    }
+}
+
+// Warp roles: warps 0-7 epilogue (thread = row (warp & 3) * 32 + lane = TMEM lane; the two warps of a lane quarter split the
+// columns), warp 8 weight producer, warp 9 MMA issuer + TMEM owner.
 template <int KS>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__restrict__ wsw, const float *__restrict__ bias,
                       const __half *__restrict__ w1, const __half *__restrict__ b1,
                       const float *__restrict__ xs, const float *__restrict__ ys, const float *__restrict__ z,
-                      int H, int W, int b0, int nb, int row0, int nrw, __half *__restrict__ psf) {
+                      int H, int W, int b0, int nb, int row0, int nrw, __half *__restrict__ psf, long long *__restrict__ dbg) {
     extern __shared__ __align__(1024) unsigned char fm_smem[];
     constexpr int KK = KS * KS;
+    constexpr int KC = (KK + 31) / 32;                       // 32-column chunks of the last layer
     unsigned char *sA = fm_smem;
     unsigned char *sW = fm_smem + OFF_W;
     float4 *sW1 = reinterpret_cast<float4 *>(fm_smem + OFF_W1);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(fm_smem + OFF_BAR), *empty = full + STAGES;
-    unsigned long long *a_ready = empty + STAGES, *acc_ready = a_ready + 1;
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(acc_ready + 1);
+    unsigned long long *a_ready = empty + STAGES, *acc_ready = a_ready + 1;          // acc_ready[2]: one per accumulator half
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(acc_ready + 2);
+    float *s_part = reinterpret_cast<float *>(sA + TM * KK * 2);                     // [4][TM] partial sums of the last layer, behind the packed block
+    static_assert(TM * KK * 2 + 4 * TM * 4 <= A_BYTES, "the packed block and its partial sums must fit in the activation tile");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = net.n_layers;
     const unsigned n_rows = 2u * (unsigned)nb * (unsigned)nrw * (unsigned)W;
@@ -119,11 +242,12 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
         sW1[i] = make_float4(__half2float(w1[3 * i]), __half2float(w1[3 * i + 1]), __half2float(w1[3 * i + 2]), __half2float(b1[i]));
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(a_ready, TM);
+        mbar_init(a_ready, EPI_THREADS);
         mbar_init(acc_ready, 1);
+        mbar_init(acc_ready + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {                                          // this warp owns the TMEM allocation (all 512 columns)
+    if (warp == MMA_WARP) {                                   // this warp owns the TMEM allocation (all 512 columns)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -132,7 +256,7 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
     tc_fence_after();
     const unsigned tmem = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == PROD_WARP) {
         // ---- weight producer: one contiguous bulk copy per (layer, half, k-block), in the order the MMA warp consumes them ----
         if (lane == 0) {
             int s = 0;
@@ -154,46 +278,59 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == MMA_WARP) {
         // ---- MMA issuer ----------------------------------------------------------------------------------------------------
         if (lane == 0) {
             int s = 0;
             unsigned ph = 0, a_ph = 0;
             const unsigned a_base = smem_u32(sA), w_base = smem_u32(sW);
+            long long t_start = clock64(), t_full = 0, t_aready = 0, t0;
             for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int l = 0; l < L; ++l) {
                     const int nkb = net.K[l] >> 6, N = net.N[l];
+                    t0 = clock64();
                     mbar_wait(a_ready, a_ph);                 // the A tile of this layer is written and TMEM is drained
+                    t_aready += clock64() - t0;
                     a_ph ^= 1u;
                     tc_fence_after();
-                    for (int h = 0; h * 256 < N; ++h) {
-                        const unsigned idesc = instr_desc(min(256, N - h * 256));
-                        const unsigned d_tmem = tmem + (unsigned)(h * 256);
-                        for (int kb = 0; kb < nkb; ++kb) {
-                            mbar_wait(full + s, ph);
-                            tc_fence_after();
+                    for (int h = 0; h < 2; ++h) {
+                        if (h * 256 < N) {
+                            const unsigned idesc = instr_desc(min(256, N - h * 256));
+                            const unsigned d_tmem = tmem + (unsigned)(h * 256);
+                            for (int kb = 0; kb < nkb; ++kb) {
+                                t0 = clock64();
+                                mbar_wait(full + s, ph);
+                                t_full += clock64() - t0;
+                                tc_fence_after();
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)       // UMMA K = 16 fp16 = 32 bytes inside the 128-byte swizzle row
-                                tc_mma_f16(d_tmem, smem_desc(a_base + kb * A_KB_BYTES + k * 32), smem_desc(w_base + s * STAGE_BYTES + k * 32),
-                                           idesc, (unsigned)((kb | k) != 0));
-                            tc_commit(empty + s);             // the stage is free once these MMAs have read it
-                            if (++s == STAGES) { s = 0; ph ^= 1u; }
+                                for (int k = 0; k < 4; ++k)   // UMMA K = 16 fp16 = 32 bytes inside the 128-byte swizzle row
+                                    tc_mma_f16(d_tmem, smem_desc(a_base + kb * A_KB_BYTES + k * 32), smem_desc(w_base + s * STAGE_BYTES + k * 32),
+                                               idesc, (unsigned)((kb | k) != 0));
+                                tc_commit(empty + s);         // the stage is free once these MMAs have read it
+                                if (++s == STAGES) { s = 0; ph ^= 1u; }
+                            }
                         }
+                        tc_commit(acc_ready + h);             // this half of the accumulator is complete (h = 1: the whole layer)
                     }
-                    tc_commit(acc_ready);                     // every MMA of the layer has completed
                 }
             }
+            if (dbg) { dbg[blockIdx.x * 8 + 0] = clock64() - t_start; dbg[blockIdx.x * 8 + 1] = t_full; dbg[blockIdx.x * 8 + 2] = t_aready; }
         }
     } else {
-        // ---- epilogue warps: thread t = row t of the tile = TMEM lane t --------------------------------------------------------
-        const int t = threadIdx.x;
-        const unsigned lane_addr = tmem + ((unsigned)(warp * 32) << 16);
+        // ---- epilogue warps --------------------------------------------------------------------------------------------------
+        const int t = (warp & 3) * 32 + lane;                 // row of the tile = TMEM lane
+        const int grp = warp >> 2;                            // which of the two warps of this lane quarter
+        const unsigned lane_addr = tmem + ((unsigned)((warp & 3) * 32) << 16);
         unsigned acc_ph = 0;
+        long long e_start = clock64(), e_wait = 0, e_last = 0, e_p0 = 0, e_st = 0, e0, e1;
         for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            // first Linear (K = 3) + ReLU for this row, straight into the swizzled A tile (mlp_input_layer_kernel's arithmetic)
+            // first Linear (K = 3) + ReLU for this row, straight into the swizzled A tile (mlp_input_layer_kernel's arithmetic);
+            // the two warps of a row take alternate groups of 8 columns
             {
-                const unsigned r = min(tile * TM + (unsigned)t, n_rows - 1);
-                const unsigned p = r >> 1, side = r & 1u;
+                // tile row t: pixel (t & 63) of the tile's 64, left kernel for t < 64, right kernel for t >= 64 (a warp is
+                // all-left or all-right: the flip of the right kernels is then a compile-time address pattern)
+                const unsigned side = (unsigned)t >> 6;
+                const unsigned p = min(tile * (TM / 2) + ((unsigned)t & 63u), (n_rows >> 1) - 1);
                 const unsigned q = p / (unsigned)W, x = p - q * (unsigned)W;
                 const unsigned bq = q / (unsigned)nrw;
                 const int y = row0 + (int)(q - bq * (unsigned)nrw), b = b0 + (int)bq;
@@ -201,7 +338,7 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 const float xv = __half2float(__float2half_rn(side ? -xr : xr));
                 const float yv = __half2float(__float2half_rn(__ldg(ys + y)));
                 const float zv = __half2float(__float2half_rn(__ldg(z + ((int64_t)b * H + y) * W + x)));
-                for (int c = 0; c < net.n1; c += 8) {
+                for (int c = 8 * grp; c < net.n1; c += 16) {
                     unsigned o[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -217,21 +354,52 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
             tc_fence_before();
             mbar_arrive(a_ready);
             for (int l = 0; l + 1 < L; ++l) {
-                // hidden layer: accumulator -> + bias -> ReLU -> fp16 -> the next layer's A operand
+                // hidden layer: accumulator -> + bias -> ReLU -> fp16 -> the next layer's A operand.  Half 0 of the accumulator
+                // is drained into registers while the MMAs of half 1 still read the A tile; once the layer is complete the
+                // registers are stored and half 1 follows.  A warp takes every second 32-column chunk of a half.
                 const int N = net.N[l];
                 const float4 *bp = reinterpret_cast<const float4 *>(bias + net.b_off[l]);
+                const int nc0 = min(256, N) >> 5, nc1 = max(N - 256, 0) >> 5;       // chunks in each half
+                unsigned held[4][16];
+                e0 = clock64();
                 mbar_wait(acc_ready, acc_ph);
+                e_wait += clock64() - e0;
+                tc_fence_after();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = 2 * i + grp;
+                    if (c < nc0) {
+                        unsigned r[32];
+                        float4 bv[8];
+                        tmem_ld32_issue(lane_addr + (unsigned)(32 * c), r);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) bv[g] = __ldg(bp + 8 * c + g);
+                        tmem_wait32(r);
+                        bias_relu_pack(r, bv, held[i]);
+                    }
+                }
+                e0 = clock64();
+                mbar_wait(acc_ready + 1, acc_ph);
+                e_wait += clock64() - e0;
                 acc_ph ^= 1u;
                 tc_fence_after();
-                for (int j = 0; j < N; j += 32) {
-                    float v[32];
-                    tmem_ld32(lane_addr + (unsigned)j, v);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const float4 ba = __ldg(bp + (j >> 2) + 2 * g), bb = __ldg(bp + (j >> 2) + 2 * g + 1);
-                        const uint4 o = make_uint4(pack_relu_h2(v[8 * g] + ba.x, v[8 * g + 1] + ba.y), pack_relu_h2(v[8 * g + 2] + ba.z, v[8 * g + 3] + ba.w),
-                                                   pack_relu_h2(v[8 * g + 4] + bb.x, v[8 * g + 5] + bb.y), pack_relu_h2(v[8 * g + 6] + bb.z, v[8 * g + 7] + bb.w));
-                        *reinterpret_cast<uint4 *>(sA + a_chunk_off(t, j + 8 * g)) = o;
+                for (int i = 0; i < 4; ++i) {
+                    const int c = 2 * i + grp;
+                    if (c < nc0) store_a_chunks(sA, t, 32 * c, held[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = 2 * i + grp;
+                    if (c < nc1) {
+                        unsigned r[32], o[16];
+                        float4 bv[8];
+                        tmem_ld32_issue(lane_addr + (unsigned)(256 + 32 * c), r);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) bv[g] = __ldg(bp + 64 + 8 * c + g);
+                        tmem_wait32(r);
+                        bias_relu_pack(r, bv, o);
+                        store_a_chunks(sA, t, 256 + 32 * c, o);
                     }
                 }
                 fence_proxy_async();
@@ -239,53 +407,66 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 mbar_arrive(a_ready);
             }
             // last layer: torch's fp16 sums (sum(-1) rounds every kernel row, the second sum(-1) rounds the total), then the
-            // normalised kernels, the right rows flipped along their last axis, staged as the packed [64, 2, KS, KS] block
+            // normalised kernels, the right rows flipped along their last axis, staged as the packed [64, 2, KS, KS] block.
+            // The two warps of a row split the columns in the middle ([0, SPLIT) and [SPLIT, 32 * KC)); a thread keeps its
+            // half of the row in registers (fp16 pairs) from the accumulator to the staged block.  Kernel-row sums are taken in
+            // column order; the one kernel row that straddles SPLIT is merged from two partial sums, and the totals of the two
+            // halves are added through shared memory (fp32 sums of a few fp16 values: exact, whatever the order).
             {
+                constexpr int HC = (KC + 1) / 2;              // 32-column chunks per thread
+                constexpr int SPLIT = 32 * HC;                // first column of the second warp
+                constexpr int U_X = (SPLIT < KK) ? SPLIT / KS : -1;                 // kernel row that straddles SPLIT ...
+                constexpr bool STRADDLE = U_X >= 0 && (SPLIT % KS) != 0;            // ... unless SPLIT is a row boundary
                 const float *bl = bias + net.b_off[L - 1];
+                e0 = clock64();
                 mbar_wait(acc_ready, acc_ph);
+                mbar_wait(acc_ready + 1, acc_ph);
                 acc_ph ^= 1u;
+                e_wait += clock64() - e0;
+                e0 = clock64();
                 tc_fence_after();
-                float tot = 0.0f, rowsum = 0.0f;
-#pragma unroll
-                for (int j = 0; j < KK; j += 32) {
-                    float v[32];
-                    tmem_ld32(lane_addr + (unsigned)j, v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = j + i;
-                        if (col < KK) {
-                            rowsum += relu_h(v[i] + __ldg(bl + col));
-                            if ((col + 1) % KS == 0) { tot += __half2float(__float2half_rn(rowsum)); rowsum = 0.0f; }
-                        }
-                    }
+                const int c_lo = grp ? SPLIT : 0;             // this thread's columns: [c_lo, c_lo + 32 * HC)
+                unsigned ra[16], rb[16];
+                const int right = t >> 6;                     // warp-uniform: rows 64..127 are right kernels
+                __half *dst = reinterpret_cast<__half *>(sA) + (size_t)(2 * (t & 63) + right) * KK;   // staged block [64 px][2][KK]
+                TailState st{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, dst, bl, lane_addr, c_lo};
+                tmem_ld16_issue(lane_addr + (unsigned)c_lo, ra);
+#define SDIRT_TAIL_PASS(PASSV)                                                                                              \
+                for (int pp = 0; pp < HC; ++pp) {                                                                           \
+                    if (grp) {                                                                                              \
+                        if (right) { tail_piece<KS, PASSV, 1, 1>(2 * pp, ra, rb, st); tail_piece<KS, PASSV, 1, 1>(2 * pp + 1, rb, ra, st); } \
+                        else { tail_piece<KS, PASSV, 1, 0>(2 * pp, ra, rb, st); tail_piece<KS, PASSV, 1, 0>(2 * pp + 1, rb, ra, st); }       \
+                    } else {                                                                                                \
+                        if (right) { tail_piece<KS, PASSV, 0, 1>(2 * pp, ra, rb, st); tail_piece<KS, PASSV, 0, 1>(2 * pp + 1, rb, ra, st); } \
+                        else { tail_piece<KS, PASSV, 0, 0>(2 * pp, ra, rb, st); tail_piece<KS, PASSV, 0, 0>(2 * pp + 1, rb, ra, st); }       \
+                    }                                                                                                       \
                 }
-                float den = __half2float(__float2half_rn(tot));
-                den = __half2float(__float2half_rn(den + 1e-9f));
-                const bool ok = den > 0.0f && den <= 65504.0f;
-                float rc = rcp_approx(ok ? den : 1.0f);
-                rc = fmaf(rc, fmaf(-den, rc, 1.0f), rc);
-                __half *dst = reinterpret_cast<__half *>(sA) + (size_t)t * KK;
-                const bool flip = t & 1;                      // tiles start at an even row: odd rows are right kernels
 #pragma unroll
-                for (int j = 0; j < KK; j += 32) {
-                    float v[32];
-                    tmem_ld32(lane_addr + (unsigned)j, v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = j + i;
-                        if (col < KK) {
-                            const float a = relu_h(v[i] + __ldg(bl + col));
-                            const float qv = a * rc;
-                            const float quo = fmaf(rc, fmaf(-den, qv, a), qv);        // IEEE a / den (div_rn's sequence)
-                            const int u = col / KS, vv = col - u * KS;
-                            dst[flip ? u * KS + (KS - 1 - vv) : col] = __float2half_rn(ok ? quo : 0.0f);
-                        }
-                    }
+                SDIRT_TAIL_PASS(0)
+                e_p0 += clock64() - e0;
+                tmem_ld16_issue(lane_addr + (unsigned)c_lo, ra);          // second pass: in flight during the exchange of the sums
+                s_part[grp * TM + t] = st.part;
+                s_part[(2 + grp) * TM + t] = st.rs_x;
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                float tot = s_part[t] + s_part[TM + t];
+                if (STRADDLE) tot += __half2float(__float2half_rn(s_part[2 * TM + t] + s_part[3 * TM + t]));
+                st.den = __half2float(__float2half_rn(tot));
+                st.den = __half2float(__float2half_rn(st.den + 1e-9f));
+                if (st.den > 0.0f && st.den <= 65504.0f) {
+                    st.rc = rcp_approx(st.den);
+                    st.rc = fmaf(st.rc, fmaf(-st.den, st.rc, 1.0f), st.rc);
+                } else {
+                    st.den = 0.0f;                            // all-zero kernel: every quotient becomes 0
+                    st.rc = 0.0f;
                 }
+#pragma unroll
+                SDIRT_TAIL_PASS(1)
+#undef SDIRT_TAIL_PASS
+                e1 = clock64();
                 tc_fence_before();
                 fence_proxy_async();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (t == 0) {
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                if (threadIdx.x == 0) {
                     const unsigned rows_here = min((unsigned)TM, n_rows - tile * TM);
                     const unsigned bytes = rows_here * (unsigned)(KK * 2);
                     __half *g = psf + (size_t)tile * TM * KK;
@@ -293,13 +474,16 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                e_last += clock64() - e0;
+                e_st += clock64() - e1;
             }
         }
+        if (dbg && threadIdx.x == 0) { dbg[blockIdx.x * 8 + 3] = clock64() - e_start; dbg[blockIdx.x * 8 + 4] = e_wait; dbg[blockIdx.x * 8 + 5] = e_last; dbg[blockIdx.x * 8 + 6] = e_p0; dbg[blockIdx.x * 8 + 7] = e_st; }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }

@@ -54,6 +54,16 @@ def main():
     flop = px * 2 * 2 * (3 * 128 + 128 * 512 + 8 * 512 * 512 + 512 * 441)
     t_f = timed(lambda: fused.pred(xs, ys, z, 0, B, 0, rows, ks))
     t_c = timed(cublas)
+    import ctypes as C
+    dbg = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+    E.lib().sdirt_mlp_fused_debug(C.c_void_p(dbg.data_ptr()))
+    fused.pred(xs, ys, z, 0, B, 0, rows, ks); torch.cuda.synchronize()
+    E.lib().sdirt_mlp_fused_debug(C.c_void_p(0))
+    d = dbg.double().cpu().numpy()
+    tiles_per_cta = (2 * px / 128) / min(148, 2 * px / 128)
+    m = d[d[:, 0] > 0].mean(0)
+    print(f"cycles per CTA: MMA loop {m[0]:.0f} (wait weights {m[1]:.0f}, wait A/epilogue {m[2]:.0f}); epilogue loop {m[3]:.0f} "
+          f"(wait accumulator {m[4]:.0f}, last-layer tail {m[5]:.0f} = pass0 {m[6]:.0f} + pass1 {m[5] - m[6] - m[7]:.0f} + barriers/store {m[7]:.0f}); tiles/CTA {tiles_per_cta:.1f}; per tile-layer {m[0] / tiles_per_cta / 10:.0f} cycles")
     print(f"fused {t_f * 1e3:.0f} us = {flop / t_f / 1e9:.0f} TFLOP/s; cuBLAS route {t_c * 1e3:.0f} us = {flop / t_c / 1e9:.0f} TFLOP/s")
 
 
