@@ -254,6 +254,10 @@ int sdirt_mlp_fused_pred(const sdirt_mlp_shape *shape, const void *packed_w_dev,
 /* Measurement helper: a device buffer [grid][8] of int64 that the next sdirt_mlp_fused_pred launches fill with cycle counters
  * (MMA loop, its waits for weights / for the epilogue; epilogue loop, its waits); NULL switches it off. */
 void sdirt_mlp_fused_debug(long long *counters_dev);
+/* Kernel variant of sdirt_mlp_fused_pred: 2 (default) = CTA pairs (thread-block cluster of 2, tcgen05 cta_group::2, each CTA
+ * stages half of every weight tile), 1 = single CTAs.  Same results either way; returns the previous setting (other values of
+ * `ncta` only query). */
+int sdirt_mlp_fused_cta_group(int ncta);
 
 /* gamma -> sensor noise -> clip(0,1), the tail of PSFNet.render(train=True) (psfnet.py:605-620, 629-642, 708-713), in
  * place on x_dev[N, 2C, H, W] (the convolved linear image, left channels first).  randn_dev: standard-normal draws of

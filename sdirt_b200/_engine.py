@@ -80,6 +80,8 @@ def lib():
     L.sdirt_mlp_fused_layout.argtypes = [C.POINTER(MlpShape), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(i64)]
     L.sdirt_mlp_fused_layout.restype = i64
     L.sdirt_mlp_fused_pack_layer.argtypes = [C.POINTER(MlpShape), cint, vp, vp, vp, vp, vp]
+    L.sdirt_mlp_fused_cta_group.argtypes = [cint]
+    L.sdirt_mlp_fused_cta_group.restype = cint
     L.sdirt_mlp_fused_pred.argtypes = [C.POINTER(MlpShape), vp, vp, vp, vp, vp, vp, vp, cint, cint, cint, cint, cint, cint, cint, cint, vp, vp]
     L.sdirt_gamma_noise_clip.argtypes = [vp, vp, vp, vp, cint, cint, cint, cint, vp]
     L.sdirt_fp32_peak_probe.argtypes = [vp, cint, cint, cint, vp]

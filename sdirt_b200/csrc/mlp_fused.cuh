@@ -28,17 +28,27 @@ namespace mlpf {
 constexpr int TM = 128;                          // rows per tile = TMEM lanes
 constexpr int A_KB_BYTES = TM * 128;             // one 64-wide k-block of the activation tile
 constexpr int A_BYTES = 8 * A_KB_BYTES;          // K <= 512
-constexpr int STAGE_BYTES = 256 * 128;           // one weight tile: <= 256 output rows x 64 k
-constexpr int STAGES = 3;
 constexpr int MAX_LAYERS = 12;
 constexpr int MAX_N1 = 128;
-constexpr int OFF_W = A_BYTES;
-constexpr int OFF_W1 = OFF_W + STAGES * STAGE_BYTES;
-constexpr int OFF_BAR = OFF_W1 + MAX_N1 * 16;
-constexpr int SMEM_BYTES = OFF_BAR + 128;                // barriers, TMEM slot
 constexpr int EPI_THREADS = 256, PROD_WARP = 8, MMA_WARP = 9;
 constexpr int THREADS = 320;
-static_assert(SMEM_BYTES <= 227 * 1024, "fused MLP tile does not fit in shared memory");
+// NCTA = 1: one CTA per tile, a weight tile [<= 256 rows x 64 k] per ring stage, biases read from global memory.
+// NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2, UMMA M = 256) works on two tiles at once; each CTA stages only ITS
+// half of every weight tile (the tensor cores of both SMs read both halves), which halves the L2 -> SM weight traffic -- the
+// bound of the 1-CTA kernel: 512 KB per tile-layer per SM against ~42 B/clk/SM of L2 throughput is 12.3 k cycles for 8.2 k
+// cycles of MMA -- and frees shared memory for a fourth stage and for all the biases.
+template <int NCTA>
+struct Cfg {
+    static constexpr int STAGE_BYTES = 256 * 128 / NCTA;
+    static constexpr int STAGES = NCTA == 1 ? 3 : 4;
+    static constexpr int BIAS_FLOATS = NCTA == 1 ? 0 : 11 * 512;     // capacity of the resident bias table
+    static constexpr int OFF_W = A_BYTES;
+    static constexpr int OFF_BIAS = OFF_W + STAGES * STAGE_BYTES;
+    static constexpr int OFF_W1 = OFF_BIAS + BIAS_FLOATS * 4;
+    static constexpr int OFF_BAR = OFF_W1 + MAX_N1 * 16;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;                  // barriers, TMEM slot
+    static_assert(SMEM_BYTES <= 227 * 1024, "fused MLP tile does not fit in shared memory");
+};
 
 struct Net {
     int n_layers;                 // tensor-core layers (everything after the first Linear)
@@ -51,21 +61,47 @@ struct Net {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// tcgen05.commit: the mbarrier is signalled once every MMA issued so far by this thread has completed; NCTA = 2: the barrier
+// at the same offset in BOTH CTAs of the pair
+template <int NCTA>
 __device__ __forceinline__ void tc_commit(unsigned long long *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    if constexpr (NCTA == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
 }
+template <int NCTA>
 __device__ __forceinline__ void tc_mma_f16(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc, unsigned acc) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    if constexpr (NCTA == 1)
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// CTA pair plumbing
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.  Default (CTA-scope) semantics on
+// purpose: the cluster-scope release / acquire forms compile to MEMBAR.ALL.GPU and CCTL.IVALL around every hand-over, and
+// what is handed over here is read by the tensor cores through the async proxy (the writers have fenced it already).
+__device__ __forceinline__ void mbar_arrive_remote(unsigned long long *bar, unsigned cta) {
+    asm volatile("{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
+                 "mbarrier.arrive.shared::cluster.b64 _, [ra];\n}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 // K-major, SWIZZLE_128B operand: 8-row atoms of 1024 B (stride byte offset), rows of 128 B, descriptor version 1 (sm_100)
 __device__ __forceinline__ unsigned long long smem_desc(unsigned addr) {
     return (unsigned long long)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16: D = f32, A = B = f16, both K-major, M = 128
-__device__ __forceinline__ unsigned instr_desc(int n) { return (1u << 4) | ((unsigned)(n >> 3) << 17) | ((unsigned)(TM >> 4) << 24); }
+// kind::f16: D = f32, A = B = f16, both K-major; m = 128 (one CTA) or 256 (CTA pair: 128 rows from each)
+__device__ __forceinline__ unsigned instr_desc(int n, int m) { return (1u << 4) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24); }
 
 // 32 consecutive fp32 columns of this thread's TMEM lane: the load is asynchronous, the registers may be read only after
 // tmem_wait32 (which names them as operands so that the compiler keeps every use behind the wait).
@@ -124,6 +160,12 @@ __device__ __forceinline__ float4 ldg_f4_here(const float4 *p) {
     return v;
 }
 
+__device__ __forceinline__ float4 lds_f4_here(const float4 *p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+
 // byte offset of the 16-byte chunk holding columns [col, col + 8) of row `row` in the swizzled activation tile
 __device__ __forceinline__ unsigned a_chunk_off(int row, int col) {
     const int kb = col >> 6, c = (col & 63) >> 3;
@@ -136,12 +178,18 @@ __device__ __forceinline__ unsigned pack_relu_h2(float a, float b) {
 }
 __device__ __forceinline__ float relu_h(float a) { return __half2float(__float2half_rn(fmaxf(a, 0.0f))); }
 
-// 32 accumulator columns + bias -> ReLU -> fp16, packed two per register
+// 32 accumulator columns + bias -> ReLU -> fp16, packed two per register: one packed fp32 add (FADD2), one conversion (F2FP)
+// and one packed maximum (HMNMX2) per pair of columns; relu(round(x)) = round(relu(x)) since rounding is monotonic
+__device__ __forceinline__ unsigned add_relu_h2(unsigned a, unsigned b, float ba, float bb) {
+    const float2 v = __fadd2_rn(make_float2(__uint_as_float(a), __uint_as_float(b)), make_float2(ba, bb));
+    const __half2 h = __hmax2(__floats2half2_rn(v.x, v.y), __float2half2_rn(0.0f));
+    return *reinterpret_cast<const unsigned *>(&h);
+}
 __device__ __forceinline__ void bias_relu_pack(const unsigned (&r)[32], const float4 (&bv)[8], unsigned (&o)[16]) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-        o[2 * g] = pack_relu_h2(__uint_as_float(r[4 * g]) + bv[g].x, __uint_as_float(r[4 * g + 1]) + bv[g].y);
-        o[2 * g + 1] = pack_relu_h2(__uint_as_float(r[4 * g + 2]) + bv[g].z, __uint_as_float(r[4 * g + 3]) + bv[g].w);
+        o[2 * g] = add_relu_h2(r[4 * g], r[4 * g + 1], bv[g].x, bv[g].y);
+        o[2 * g + 1] = add_relu_h2(r[4 * g + 2], r[4 * g + 3], bv[g].z, bv[g].w);
     }
 }
 __device__ __forceinline__ void store_a_chunks(unsigned char *sA, int row, int col, const unsigned (&o)[16]) {
@@ -150,85 +198,121 @@ __device__ __forceinline__ void store_a_chunks(unsigned char *sA, int row, int c
         *reinterpret_cast<uint4 *>(sA + a_chunk_off(row, col + 8 * g)) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
 }
 
-// Last layer, one 16-column piece of the accumulator: relu(acc + bias) rounded to fp16 (two values per F2FP / HMNMX2).
-// PASS 0 adds it to the kernel-row sums, PASS 1 (the accumulator is read a second time: TMEM loads are cheap, a hundred
-// live registers are not) divides and stages the result at its final position.  The next piece is in flight while this one
-// is used.  GRP: which half of the columns (split at SPLIT) this warp owns; RIGHT: the warp's rows are right kernels (rows
-// 64..127 of a tile), whose columns are flipped inside every kernel row -- both compile-time, so every staged address is
-// an immediate.
+// Last layer, one 16-column piece [col0, col0 + 16) of this thread's half row of the accumulator: relu(acc + bias) rounded to
+// fp16.  PASS 0 adds it to the kernel-row sums, PASS 1 (the accumulator is read a second time: TMEM loads are cheap, a
+// hundred live registers are not) divides and stages the result at its final position; RIGHT: the warp's rows are right
+// kernels (rows 64..127 of a tile), whose columns are flipped inside every kernel row.  The position of the piece is a
+// run-time value on purpose: unrolling the row over compile-time columns (every address an immediate) made 12 k instructions
+// of straight-line code per kernel, four times the instruction cache, and the tail ran at the speed of instruction fetch.
 struct TailState {
     float part, rs, rs_x, den, rc;      // total of finished kernel rows, running row, the straddling row's piece; denominator
     __half *dst;                        // this row of the staged block
-    const float *bl;                    // last layer's bias
+    const float *bl;                    // last layer's bias (SB: in shared memory)
     unsigned lane_addr;
-    int c_lo;
+    int c_lo, c_end;                    // this thread's live columns
 };
-template <int KS, int PASS, int GRP, int RIGHT>
-__device__ __forceinline__ void tail_piece(const int hcx, unsigned (&cur)[16], unsigned (&nxt)[16], TailState &st) {
+template <int KS>
+__device__ __forceinline__ int wrap_ks(int w) {              // w mod KS for w < KS + 16
+#pragma unroll
+    for (int k = 0; k < (16 + KS - 1) / KS; ++k) w = w >= KS ? w - KS : w;
+    return w;
+}
+template <int KS, int PASS, int RIGHT, bool SB>
+__device__ __forceinline__ void tail_piece(const int col0, const int w0 /* col0 mod KS */, const unsigned (&cur)[16], TailState &st) {
     constexpr int KK = KS * KS, KC = (KK + 31) / 32, HC = (KC + 1) / 2, SPLIT = 32 * HC;
     constexpr int U_X = (SPLIT < KK) ? SPLIT / KS : -1;
     constexpr bool STRADDLE = U_X >= 0 && (SPLIT % KS) != 0;
-    float4 bv[4];                                             // this piece's biases (the padded bias row covers every chunk)
+    float4 bv[4];                                             // this piece's biases (the padded bias row covers every piece)
 #pragma unroll
-    for (int g = 0; g < 4; ++g) bv[g] = ldg_f4_here(reinterpret_cast<const float4 *>(st.bl + st.c_lo + 16 * hcx) + g);
-    tmem_wait16(cur);
-    if (hcx + 1 < 2 * HC) tmem_ld16_issue_after(st.lane_addr + (unsigned)(st.c_lo + 16 * (hcx + 1)), nxt, cur);
+    for (int g = 0; g < 4; ++g) {
+        const float4 *bp = reinterpret_cast<const float4 *>(st.bl + col0) + g;
+        bv[g] = SB ? lds_f4_here(bp) : ldg_f4_here(bp);
+    }
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
-        const int col = (GRP ? SPLIT : 0) + 16 * hcx + i;     // a compile-time constant once hcx is unrolled
-        const bool live0 = GRP ? (col < KK) : (col < KK && col < SPLIT);
-        const bool live1 = GRP ? (col + 1 < KK) : (col + 1 < KK && col + 1 < SPLIT);
-        if (!live0) continue;
+        const int c0 = col0 + i;                              // even: col0 is a multiple of 16
+        const bool live0 = c0 < st.c_end, live1 = c0 + 1 < st.c_end;
         const float b0 = (i & 2) ? bv[i >> 2].z : bv[i >> 2].x, b1 = (i & 2) ? bv[i >> 2].w : bv[i >> 2].y;
         // relu(round_fp16(acc + bias)) for two columns at once
-        const __half2 h = __hmax2(__floats2half2_rn(__uint_as_float(cur[i]) + b0, __uint_as_float(cur[i + 1]) + b1), __float2half2_rn(0.0f));
-        const float v0 = __low2float(h), v1 = live1 ? __high2float(h) : 0.0f;
+        const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), make_float2(b0, b1));
+        const __half2 h = __hmax2(__floats2half2_rn(s2.x, s2.y), __float2half2_rn(0.0f));
+        const float v0 = live0 ? __low2float(h) : 0.0f, v1 = live1 ? __high2float(h) : 0.0f;
+        const int wa = wrap_ks<KS>(w0 + i), wb = wrap_ks<KS>(w0 + i + 1);       // positions inside their kernel rows
         if (PASS == 0) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                if (k == 1 && !live1) break;
-                const int c = col + k;
+                const int c = c0 + k;
                 st.rs += k ? v1 : v0;
-                // end of a kernel row (or of this thread's piece of the straddling row)
-                if (((c + 1) % KS == 0) || (!GRP && c + 1 == SPLIT) || (c + 1 == KK)) {
-                    if (STRADDLE && c / KS == U_X) st.rs_x = st.rs;
+                // end of a kernel row (or of this thread's piece of the straddling row); warp-uniform
+                if ((k ? live1 : live0) && ((k ? wb : wa) == KS - 1 || c + 1 == st.c_end)) {
+                    if (STRADDLE && c >= U_X * KS && c < (U_X + 1) * KS) st.rs_x = st.rs;
                     else st.part += __half2float(__float2half_rn(st.rs));
                     st.rs = 0.0f;
                 }
             }
         } else {
             // IEEE v / den from the refined reciprocal (div_rn's sequence); den = rc = 0 for an all-zero kernel -> 0
-            const float q0 = v0 * st.rc, q1 = v1 * st.rc;
-            const float r0 = fmaf(st.rc, fmaf(-st.den, q0, v0), q0), r1 = fmaf(st.rc, fmaf(-st.den, q1, v1), q1);
-            const int u0 = col / KS, w0 = col - u0 * KS, u1 = (col + 1) / KS, w1 = (col + 1) - u1 * KS;
-            const int p0 = RIGHT ? u0 * KS + (KS - 1 - w0) : col, p1 = RIGHT ? u1 * KS + (KS - 1 - w1) : col + 1;
-            if (!RIGHT && live1 && (col & 1) == 0) {          // left rows start 4-byte aligned: one 32-bit store per pair
-                const __half2 o = __floats2half2_rn(r0, r1);
-                *reinterpret_cast<__half2 *>(st.dst + col) = o;
-            } else {
-                st.dst[p0] = __float2half_rn(r0);
-                if (live1) st.dst[p1] = __float2half_rn(r1);
+            const float2 rc2 = make_float2(st.rc, st.rc), v2 = make_float2(v0, v1);
+            const float2 q = __fmul2_rn(v2, rc2);
+            const float2 r = __ffma2_rn(rc2, __ffma2_rn(make_float2(-st.den, -st.den), q, v2), q);
+            if (!RIGHT) {                                     // left rows start 4-byte aligned: one 32-bit store per pair
+                if (live1) *reinterpret_cast<__half2 *>(st.dst + c0) = __floats2half2_rn(r.x, r.y);
+                else if (live0) st.dst[c0] = __float2half_rn(r.x);
+            } else {                                          // column w of a kernel row goes to KS - 1 - w
+                if (live0) st.dst[c0 + (KS - 1) - 2 * wa] = __float2half_rn(r.x);
+                if (live1) st.dst[c0 + 1 + (KS - 1) - 2 * wb] = __float2half_rn(r.y);
             }
         }
     }
 }
+// One pass over this thread's half row: 2 * HC pieces, the next one in flight while the current one is used (the two
+// register arrays alternate, so an iteration handles two pieces); the loop is NOT unrolled (see tail_piece).
+template <int KS, int PASS, int RIGHT, bool SB>
+__device__ __forceinline__ void tail_pass(TailState &st) {
+    constexpr int KK = KS * KS, KC = (KK + 31) / 32, HC = (KC + 1) / 2;
+    unsigned ra[16], rb[16];
+    int w = st.c_lo % KS;
+    tmem_ld16_issue(st.lane_addr + (unsigned)st.c_lo, ra);
+#pragma unroll 1
+    for (int pc = 0; pc < HC; ++pc) {
+        const int col0 = st.c_lo + 32 * pc;
+        tmem_wait16(ra);
+        tmem_ld16_issue_after(st.lane_addr + (unsigned)(col0 + 16), rb, ra);
+        tail_piece<KS, PASS, RIGHT, SB>(col0, w, ra, st);
+        w = wrap_ks<KS>(w + 16);
+        tmem_wait16(rb);
+        if (pc + 1 < HC) tmem_ld16_issue_after(st.lane_addr + (unsigned)(col0 + 32), ra, rb);
+        tail_piece<KS, PASS, RIGHT, SB>(col0 + 16, w, rb, st);
+        w = wrap_ks<KS>(w + 16);
+    }
+}
 
 // Warp roles: warps 0-7 epilogue (thread = row (warp & 3) * 32 + lane = TMEM lane; the two warps of a lane quarter split the
-// columns), warp 8 weight producer, warp 9 MMA issuer + TMEM owner.
-template <int KS>
+// columns), warp 8 weight producer, warp 9 MMA issuer + TMEM owner (NCTA = 2: the leader CTA's warp 9 issues for the pair, the
+// other CTA's warp 9 relays its CTA's "operand ready" barriers to the leader).
+//
+// Hand-over of the activation tile between layers (a_lo / a_hi): the epilogue drains accumulator half 0 (output columns
+// 0..255 = k-blocks 0..3 of the next layer) into registers while the MMAs of half 1 still read the A tile; when the layer is
+// complete it stores them and signals a_lo, and the next layer's MMAs over k-blocks 0..3 run while the epilogue converts half
+// 1 (k-blocks 4..7, signalled by a_hi).
+template <int KS, int NCTA>
 __global__ void __launch_bounds__(THREADS, 1)
-mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__restrict__ wsw, const float *__restrict__ bias,
+mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__restrict__ wsw, const float *__restrict__ bias, int bias_floats,
                       const __half *__restrict__ w1, const __half *__restrict__ b1,
                       const float *__restrict__ xs, const float *__restrict__ ys, const float *__restrict__ z,
                       int H, int W, int b0, int nb, int row0, int nrw, __half *__restrict__ psf, long long *__restrict__ dbg) {
     extern __shared__ __align__(1024) unsigned char fm_smem[];
+    using CF = Cfg<NCTA>;
+    constexpr int STAGES = CF::STAGES, STAGE_BYTES = CF::STAGE_BYTES;
+    constexpr bool SB = NCTA == 2;                           // biases resident in shared memory
     constexpr int KK = KS * KS;
     constexpr int KC = (KK + 31) / 32;                       // 32-column chunks of the last layer
     unsigned char *sA = fm_smem;
-    unsigned char *sW = fm_smem + OFF_W;
-    float4 *sW1 = reinterpret_cast<float4 *>(fm_smem + OFF_W1);
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(fm_smem + OFF_BAR), *empty = full + STAGES;
-    unsigned long long *a_ready = empty + STAGES, *acc_ready = a_ready + 1;          // acc_ready[2]: one per accumulator half
+    unsigned char *sW = fm_smem + CF::OFF_W;
+    float *sBias = reinterpret_cast<float *>(fm_smem + CF::OFF_BIAS);
+    float4 *sW1 = reinterpret_cast<float4 *>(fm_smem + CF::OFF_W1);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(fm_smem + CF::OFF_BAR), *empty = full + STAGES;
+    unsigned long long *a_lo = empty + STAGES, *a_hi = a_lo + 1, *acc_ready = a_hi + 1;     // acc_ready[2]: one per accumulator half
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(acc_ready + 2);
     float *s_part = reinterpret_cast<float *>(sA + TM * KK * 2);                     // [4][TM] partial sums of the last layer, behind the packed block
     static_assert(TM * KK * 2 + 4 * TM * 4 <= A_BYTES, "the packed block and its partial sums must fit in the activation tile");
@@ -236,41 +320,54 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
     const int L = net.n_layers;
     const unsigned n_rows = 2u * (unsigned)nb * (unsigned)nrw * (unsigned)W;
     const unsigned n_tiles = (n_rows + TM - 1) / TM;
+    const unsigned rank = NCTA == 2 ? cluster_ctarank() : 0u;
+    // a CTA (pair) takes tile group g = its index, g + number of CTAs (pairs), ...; the CTA of rank r works on tile NCTA * g + r
+    // (a pair's second tile may lie past the end: it is computed on clamped coordinates and not stored)
+    const unsigned n_groups = (n_tiles + NCTA - 1) / NCTA, g0 = blockIdx.x / NCTA, g_step = gridDim.x / NCTA;
 
     if ((smem_u32(fm_smem) & 1023u) != 0) __trap();         // the swizzled operand atoms need a 1024-byte aligned base
     for (int i = threadIdx.x; i < net.n1; i += blockDim.x)
         sW1[i] = make_float4(__half2float(w1[3 * i]), __half2float(w1[3 * i + 1]), __half2float(w1[3 * i + 2]), __half2float(b1[i]));
+    if (SB) for (int i = threadIdx.x; i < bias_floats; i += blockDim.x) sBias[i] = bias[i];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(a_ready, EPI_THREADS);
+        const unsigned peer = (NCTA == 2 && rank == 0) ? 1u : 0u;      // the leader's barriers also count the other CTA's relay
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1 + peer); mbar_init(empty + s, 1); }
+        mbar_init(a_lo, EPI_THREADS + peer);
+        mbar_init(a_hi, EPI_THREADS + peer);
         mbar_init(acc_ready, 1);
         mbar_init(acc_ready + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {                                   // this warp owns the TMEM allocation (all 512 columns)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (NCTA == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (NCTA == 2) { __syncthreads(); cluster_sync_all(); } else __syncthreads();
     tc_fence_after();
     const unsigned tmem = *tmem_slot;
 
     if (warp == PROD_WARP) {
-        // ---- weight producer: one contiguous bulk copy per (layer, half, k-block), in the order the MMA warp consumes them ----
+        // ---- weight producer: one contiguous bulk copy per (layer, half, k-block), in the order the MMA warp consumes them; a
+        // CTA of a pair copies rows [rank * rows / 2, (rank + 1) * rows / 2) of the tile ----
         if (lane == 0) {
             int s = 0;
             unsigned ph = 0;
-            for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (unsigned g = g0; g < n_groups; g += g_step) {
                 for (int l = 0; l < L; ++l) {
                     const int nkb = net.K[l] >> 6, N = net.N[l];
                     const unsigned char *src = wsw + net.w_off[l];
                     for (int h = 0; h * 256 < N; ++h) {
-                        const unsigned bytes = (unsigned)min(256, N - h * 256) * 128u;
+                        const unsigned bytes = (unsigned)min(256, N - h * 256) * 128u, mine = bytes / NCTA;
                         for (int kb = 0; kb < nkb; ++kb) {
                             mbar_wait(empty + s, ph ^ 1u);
-                            mbar_expect_tx(full + s, bytes);
-                            bulk_g2s(sW + s * STAGE_BYTES, src, bytes, full + s);
+                            mbar_expect_tx(full + s, mine);
+                            bulk_g2s(sW + s * STAGE_BYTES, src + rank * mine, mine, full + s);
                             src += bytes;
                             if (++s == STAGES) { s = 0; ph ^= 1u; }
                         }
@@ -279,42 +376,77 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
             }
         }
     } else if (warp == MMA_WARP) {
-        // ---- MMA issuer ----------------------------------------------------------------------------------------------------
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
+            // ---- MMA issuer (NCTA = 2: for both CTAs of the pair) ---------------------------------------------------------------
             int s = 0;
             unsigned ph = 0, a_ph = 0;
             const unsigned a_base = smem_u32(sA), w_base = smem_u32(sW);
             long long t_start = clock64(), t_full = 0, t_aready = 0, t0;
-            for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (unsigned g = g0; g < n_groups; g += g_step) {
                 for (int l = 0; l < L; ++l) {
-                    const int nkb = net.K[l] >> 6, N = net.N[l];
+                    const int nkb = net.K[l] >> 6, N = net.N[l], kb_lo = min(4, nkb);
+                    const bool tl = dbg && blockIdx.x == 0 && g == g0 + g_step;    // timeline of this CTA's second tile group
+                    long long *tlp = dbg + 148 * 8 + l * 16;
                     t0 = clock64();
-                    mbar_wait(a_ready, a_ph);                 // the A tile of this layer is written and TMEM is drained
+                    // k-blocks [0, kb_lo) of this layer's A tile are written and accumulator half 0 is drained
+                    mbar_wait(a_lo, a_ph);
+                    if (kb_lo == nkb) mbar_wait(a_hi, a_ph);
                     t_aready += clock64() - t0;
-                    a_ph ^= 1u;
+                    if (tl) { tlp[0] = t0; tlp[1] = clock64(); }
                     tc_fence_after();
                     for (int h = 0; h < 2; ++h) {
                         if (h * 256 < N) {
-                            const unsigned idesc = instr_desc(min(256, N - h * 256));
+                            const unsigned idesc = instr_desc(min(256, N - h * 256), TM * NCTA);
                             const unsigned d_tmem = tmem + (unsigned)(h * 256);
                             for (int kb = 0; kb < nkb; ++kb) {
+                                if (h == 0 && kb == kb_lo) {  // the rest of the A tile, and accumulator half 1 drained
+                                    t0 = clock64();
+                                    mbar_wait(a_hi, a_ph);
+                                    t_aready += clock64() - t0;
+                                    if (tl) { tlp[2] = t0; tlp[3] = clock64(); }
+                                    tc_fence_after();
+                                }
                                 t0 = clock64();
                                 mbar_wait(full + s, ph);
                                 t_full += clock64() - t0;
                                 tc_fence_after();
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)   // UMMA K = 16 fp16 = 32 bytes inside the 128-byte swizzle row
-                                    tc_mma_f16(d_tmem, smem_desc(a_base + kb * A_KB_BYTES + k * 32), smem_desc(w_base + s * STAGE_BYTES + k * 32),
-                                               idesc, (unsigned)((kb | k) != 0));
-                                tc_commit(empty + s);         // the stage is free once these MMAs have read it
+                                    tc_mma_f16<NCTA>(d_tmem, smem_desc(a_base + kb * A_KB_BYTES + k * 32), smem_desc(w_base + s * STAGE_BYTES + k * 32),
+                                                     idesc, (unsigned)((kb | k) != 0));
+                                tc_commit<NCTA>(empty + s);   // the stage is free once these MMAs have read it
                                 if (++s == STAGES) { s = 0; ph ^= 1u; }
                             }
                         }
-                        tc_commit(acc_ready + h);             // this half of the accumulator is complete (h = 1: the whole layer)
+                        tc_commit<NCTA>(acc_ready + h);       // this half of the accumulator is complete (h = 1: the whole layer)
+                        if (tl) tlp[4 + h] = clock64();
                     }
+                    a_ph ^= 1u;
                 }
             }
             if (dbg) { dbg[blockIdx.x * 8 + 0] = clock64() - t_start; dbg[blockIdx.x * 8 + 1] = t_full; dbg[blockIdx.x * 8 + 2] = t_aready; }
+        } else if (NCTA == 2 && lane == 0) {
+            // ---- relay (second CTA of a pair): pass this CTA's "A tile written" and "weights landed" on to the leader's barriers,
+            // in the order the leader waits for them ----
+            int s = 0;
+            unsigned ph = 0, a_ph = 0;
+            for (unsigned g = g0; g < n_groups; g += g_step) {
+                for (int l = 0; l < L; ++l) {
+                    const int nkb = net.K[l] >> 6, N = net.N[l], kb_lo = min(4, nkb);
+                    mbar_wait(a_lo, a_ph);
+                    mbar_arrive_remote(a_lo, 0);
+                    if (kb_lo == nkb) { mbar_wait(a_hi, a_ph); mbar_arrive_remote(a_hi, 0); }
+                    for (int h = 0; h * 256 < N; ++h) {
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            if (h == 0 && kb == kb_lo) { mbar_wait(a_hi, a_ph); mbar_arrive_remote(a_hi, 0); }
+                            mbar_wait(full + s, ph);
+                            mbar_arrive_remote(full + s, 0);
+                            if (++s == STAGES) { s = 0; ph ^= 1u; }
+                        }
+                    }
+                    a_ph ^= 1u;
+                }
+            }
         }
     } else {
         // ---- epilogue warps --------------------------------------------------------------------------------------------------
@@ -323,7 +455,8 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
         const unsigned lane_addr = tmem + ((unsigned)((warp & 3) * 32) << 16);
         unsigned acc_ph = 0;
         long long e_start = clock64(), e_wait = 0, e_last = 0, e_p0 = 0, e_st = 0, e0, e1;
-        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (unsigned g = g0; g < n_groups; g += g_step) {
+            const unsigned tile = NCTA * g + rank;
             // first Linear (K = 3) + ReLU for this row, straight into the swizzled A tile (mlp_input_layer_kernel's arithmetic);
             // the two warps of a row take alternate groups of 8 columns
             {
@@ -352,18 +485,21 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
             }
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(a_ready);
+            mbar_arrive(a_lo);
+            mbar_arrive(a_hi);
             for (int l = 0; l + 1 < L; ++l) {
-                // hidden layer: accumulator -> + bias -> ReLU -> fp16 -> the next layer's A operand.  Half 0 of the accumulator
-                // is drained into registers while the MMAs of half 1 still read the A tile; once the layer is complete the
-                // registers are stored and half 1 follows.  A warp takes every second 32-column chunk of a half.
+                // hidden layer: accumulator -> + bias -> ReLU -> fp16 -> the next layer's A operand.  A warp takes every second
+                // 32-column chunk of a half.
                 const int N = net.N[l];
-                const float4 *bp = reinterpret_cast<const float4 *>(bias + net.b_off[l]);
+                const float4 *bp = reinterpret_cast<const float4 *>((SB ? sBias : bias) + net.b_off[l]);
                 const int nc0 = min(256, N) >> 5, nc1 = max(N - 256, 0) >> 5;       // chunks in each half
                 unsigned held[4][16];
+                const bool tl = dbg && blockIdx.x == 0 && threadIdx.x == 0 && g == g0 + g_step;
+                long long *tlp = dbg + 148 * 8 + l * 16 + 8;
                 e0 = clock64();
                 mbar_wait(acc_ready, acc_ph);
                 e_wait += clock64() - e0;
+                if (tl) { tlp[0] = e0; tlp[1] = clock64(); }
                 tc_fence_after();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -373,7 +509,7 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                         float4 bv[8];
                         tmem_ld32_issue(lane_addr + (unsigned)(32 * c), r);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) bv[g] = __ldg(bp + 8 * c + g);
+                        for (int g4 = 0; g4 < 8; ++g4) bv[g4] = SB ? bp[8 * c + g4] : __ldg(bp + 8 * c + g4);
                         tmem_wait32(r);
                         bias_relu_pack(r, bv, held[i]);
                     }
@@ -381,6 +517,7 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 e0 = clock64();
                 mbar_wait(acc_ready + 1, acc_ph);
                 e_wait += clock64() - e0;
+                if (tl) { tlp[2] = e0; tlp[3] = clock64(); }
                 acc_ph ^= 1u;
                 tc_fence_after();
 #pragma unroll
@@ -388,6 +525,10 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                     const int c = 2 * i + grp;
                     if (c < nc0) store_a_chunks(sA, t, 32 * c, held[i]);
                 }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(a_lo);
+                if (tl) tlp[4] = clock64();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = 2 * i + grp;
@@ -396,7 +537,7 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                         float4 bv[8];
                         tmem_ld32_issue(lane_addr + (unsigned)(256 + 32 * c), r);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) bv[g] = __ldg(bp + 64 + 8 * c + g);
+                        for (int g4 = 0; g4 < 8; ++g4) bv[g4] = SB ? bp[64 + 8 * c + g4] : __ldg(bp + 64 + 8 * c + g4);
                         tmem_wait32(r);
                         bias_relu_pack(r, bv, o);
                         store_a_chunks(sA, t, 256 + 32 * c, o);
@@ -404,7 +545,8 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 }
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(a_ready);
+                mbar_arrive(a_hi);
+                if (tl) tlp[5] = clock64();
             }
             // last layer: torch's fp16 sums (sum(-1) rounds every kernel row, the second sum(-1) rounds the total), then the
             // normalised kernels, the right rows flipped along their last axis, staged as the packed [64, 2, KS, KS] block.
@@ -417,7 +559,7 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 constexpr int SPLIT = 32 * HC;                // first column of the second warp
                 constexpr int U_X = (SPLIT < KK) ? SPLIT / KS : -1;                 // kernel row that straddles SPLIT ...
                 constexpr bool STRADDLE = U_X >= 0 && (SPLIT % KS) != 0;            // ... unless SPLIT is a row boundary
-                const float *bl = bias + net.b_off[L - 1];
+                const float *bl = (SB ? sBias : bias) + net.b_off[L - 1];
                 e0 = clock64();
                 mbar_wait(acc_ready, acc_ph);
                 mbar_wait(acc_ready + 1, acc_ph);
@@ -425,26 +567,13 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 e_wait += clock64() - e0;
                 e0 = clock64();
                 tc_fence_after();
-                const int c_lo = grp ? SPLIT : 0;             // this thread's columns: [c_lo, c_lo + 32 * HC)
-                unsigned ra[16], rb[16];
+                const int c_lo = grp ? SPLIT : 0;             // this thread's columns: [c_lo, c_lo + 32 * HC), live below c_end
+                const int c_end = grp ? KK : (SPLIT < KK ? SPLIT : KK);
                 const int right = t >> 6;                     // warp-uniform: rows 64..127 are right kernels
                 __half *dst = reinterpret_cast<__half *>(sA) + (size_t)(2 * (t & 63) + right) * KK;   // staged block [64 px][2][KK]
-                TailState st{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, dst, bl, lane_addr, c_lo};
-                tmem_ld16_issue(lane_addr + (unsigned)c_lo, ra);
-#define SDIRT_TAIL_PASS(PASSV)                                                                                              \
-                for (int pp = 0; pp < HC; ++pp) {                                                                           \
-                    if (grp) {                                                                                              \
-                        if (right) { tail_piece<KS, PASSV, 1, 1>(2 * pp, ra, rb, st); tail_piece<KS, PASSV, 1, 1>(2 * pp + 1, rb, ra, st); } \
-                        else { tail_piece<KS, PASSV, 1, 0>(2 * pp, ra, rb, st); tail_piece<KS, PASSV, 1, 0>(2 * pp + 1, rb, ra, st); }       \
-                    } else {                                                                                                \
-                        if (right) { tail_piece<KS, PASSV, 0, 1>(2 * pp, ra, rb, st); tail_piece<KS, PASSV, 0, 1>(2 * pp + 1, rb, ra, st); } \
-                        else { tail_piece<KS, PASSV, 0, 0>(2 * pp, ra, rb, st); tail_piece<KS, PASSV, 0, 0>(2 * pp + 1, rb, ra, st); }       \
-                    }                                                                                                       \
-                }
-#pragma unroll
-                SDIRT_TAIL_PASS(0)
+                TailState st{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, dst, bl, lane_addr, c_lo, c_end};
+                tail_pass<KS, 0, 0, SB>(st);
                 e_p0 += clock64() - e0;
-                tmem_ld16_issue(lane_addr + (unsigned)c_lo, ra);          // second pass: in flight during the exchange of the sums
                 s_part[grp * TM + t] = st.part;
                 s_part[(2 + grp) * TM + t] = st.rs_x;
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
@@ -459,18 +588,16 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                     st.den = 0.0f;                            // all-zero kernel: every quotient becomes 0
                     st.rc = 0.0f;
                 }
-#pragma unroll
-                SDIRT_TAIL_PASS(1)
-#undef SDIRT_TAIL_PASS
+                if (right) tail_pass<KS, 1, 1, SB>(st); else tail_pass<KS, 1, 0, SB>(st);
                 e1 = clock64();
                 tc_fence_before();
                 fence_proxy_async();
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-                if (threadIdx.x == 0) {
+                if (threadIdx.x == 0 && tile < n_tiles) {
                     const unsigned rows_here = min((unsigned)TM, n_rows - tile * TM);
                     const unsigned bytes = rows_here * (unsigned)(KK * 2);
-                    __half *g = psf + (size_t)tile * TM * KK;
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(smem_u32(sA)), "r"(bytes) : "memory");
+                    __half *gp = psf + (size_t)tile * TM * KK;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gp), "r"(smem_u32(sA)), "r"(bytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
@@ -483,9 +610,11 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all();             // the other CTA may still be signalling this one's barriers
     if (warp == MMA_WARP) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+        if constexpr (NCTA == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
 }
 

@@ -38,33 +38,42 @@ def main():
     want = cublas()
     fused = lens._mlp_fused()
     torch.cuda.synchronize()
-    print("packed weights", fused.packed_w.numel(), "bytes; launching fused kernel", flush=True)
-    got = fused.pred(xs, ys, z, 0, B, 0, rows, ks)
-    torch.cuda.synchronize()
-    d = (got.float() - want.float()).abs()
-    scale = want.float().abs().max().item()
-    print(f"P={B * rows * W} px: max |fused - cublas| = {d.max().item():.3e} (max value {scale:.3e}), mean {d.mean().item():.3e}, "
-          f"exact {float((got == want).float().mean()):.4f}, nan {int(torch.isnan(got.float()).sum())}")
-    bad = (d > 2e-2 * scale).nonzero()
-    if len(bad):
-        print("first mismatches (pixel, side, u, v):", bad[:8].tolist())
-        p0 = bad[0][0].item()
-        print("got ", got[p0, 0, 0, :8].tolist()); print("want", want[p0, 0, 0, :8].tolist())
+    import ctypes as C
     px = B * rows * W
     flop = px * 2 * 2 * (3 * 128 + 128 * 512 + 8 * 512 * 512 + 512 * 441)
-    t_f = timed(lambda: fused.pred(xs, ys, z, 0, B, 0, rows, ks))
     t_c = timed(cublas)
-    import ctypes as C
-    dbg = torch.zeros((148, 8), dtype=torch.int64, device=dev)
-    E.lib().sdirt_mlp_fused_debug(C.c_void_p(dbg.data_ptr()))
-    fused.pred(xs, ys, z, 0, B, 0, rows, ks); torch.cuda.synchronize()
-    E.lib().sdirt_mlp_fused_debug(C.c_void_p(0))
-    d = dbg.double().cpu().numpy()
-    tiles_per_cta = (2 * px / 128) / min(148, 2 * px / 128)
-    m = d[d[:, 0] > 0].mean(0)
-    print(f"cycles per CTA: MMA loop {m[0]:.0f} (wait weights {m[1]:.0f}, wait A/epilogue {m[2]:.0f}); epilogue loop {m[3]:.0f} "
-          f"(wait accumulator {m[4]:.0f}, last-layer tail {m[5]:.0f} = pass0 {m[6]:.0f} + pass1 {m[5] - m[6] - m[7]:.0f} + barriers/store {m[7]:.0f}); tiles/CTA {tiles_per_cta:.1f}; per tile-layer {m[0] / tiles_per_cta / 10:.0f} cycles")
-    print(f"fused {t_f * 1e3:.0f} us = {flop / t_f / 1e9:.0f} TFLOP/s; cuBLAS route {t_c * 1e3:.0f} us = {flop / t_c / 1e9:.0f} TFLOP/s")
+    for ncta in [int(v) for v in os.environ.get("NCTA", "2,1").split(",")]:
+        E.lib().sdirt_mlp_fused_cta_group(ncta)
+        print(f"--- {ncta} CTA(s) per tile group; packed weights {fused.packed_w.numel()} bytes; launching", flush=True)
+        got = fused.pred(xs, ys, z, 0, B, 0, rows, ks)
+        torch.cuda.synchronize()
+        d = (got.float() - want.float()).abs()
+        scale = want.float().abs().max().item()
+        print(f"P={px} px: max |fused - cublas| = {d.max().item():.3e} (max value {scale:.3e}), mean {d.mean().item():.3e}, "
+              f"exact {float((got == want).float().mean()):.4f}, nan {int(torch.isnan(got.float()).sum())}", flush=True)
+        bad = (d > 2e-2 * scale).nonzero()
+        if len(bad):
+            print("first mismatches (pixel, side, u, v):", bad[:8].tolist())
+            p0 = bad[0][0].item()
+            print("got ", got[p0, 0, 0, :8].tolist()); print("want", want[p0, 0, 0, :8].tolist())
+        t_f = timed(lambda: fused.pred(xs, ys, z, 0, B, 0, rows, ks))
+        dbg = torch.zeros((148 * 8 + 16 * 16,), dtype=torch.int64, device=dev)
+        E.lib().sdirt_mlp_fused_debug(C.c_void_p(dbg.data_ptr()))
+        fused.pred(xs, ys, z, 0, B, 0, rows, ks); torch.cuda.synchronize()
+        E.lib().sdirt_mlp_fused_debug(C.c_void_p(0))
+        tl = dbg[148 * 8:].cpu().numpy().reshape(16, 16)
+        d = dbg[:148 * 8].view(148, 8).double().cpu().numpy()
+        groups = 2 * px / 128 / ncta
+        tiles_per_cta = groups / min(148 // ncta, groups)
+        m, e = d[d[:, 0] > 0].mean(0), d[d[:, 3] > 0].mean(0)
+        print(f"cycles per CTA: MMA loop {m[0]:.0f} (wait weights {m[1]:.0f}, wait A/epilogue {m[2]:.0f}); epilogue loop {e[3]:.0f} "
+              f"(wait accumulator {e[4]:.0f}, last-layer tail {e[5]:.0f} = pass0 {e[6]:.0f} + pass1 {e[5] - e[6] - e[7]:.0f} + barriers/store {e[7]:.0f}); tiles/CTA {tiles_per_cta:.1f}; per tile-layer {m[0] / tiles_per_cta / 10:.0f} cycles")
+        t00 = tl[0, 0]
+        print("timeline of CTA 0, second tile group (cycles from the first a_lo wait; MMA thread | epilogue thread 0):")
+        for l in range(10):
+            r = tl[l] - t00
+            print(f"  layer {l}: MMA wait a_lo {r[0]}..{r[1]}, wait a_hi {r[2]}..{r[3]}, issued h0 {r[4]}, h1 {r[5]} | epi wait acc0 {r[8]}..{r[9]}, E0 done/wait acc1 {r[10]}..{r[11]}, a_lo arrive {r[12]}, a_hi arrive {r[13]}")
+        print(f"fused {t_f * 1e3:.0f} us = {flop / t_f / 1e9:.0f} TFLOP/s; cuBLAS route {t_c * 1e3:.0f} us = {flop / t_c / 1e9:.0f} TFLOP/s", flush=True)
 
 
 main()
