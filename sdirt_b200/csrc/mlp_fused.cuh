@@ -124,31 +124,39 @@ __device__ __forceinline__ void tmem_wait32(unsigned (&r)[32]) {
           TM_RW(23), TM_RW(24), TM_RW(25), TM_RW(26), TM_RW(27), TM_RW(28), TM_RW(29), TM_RW(30), TM_RW(31)
         :: "memory");
 }
-__device__ __forceinline__ void tmem_ld16_issue(unsigned taddr, unsigned (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : TM_R(0), TM_R(1), TM_R(2), TM_R(3), TM_R(4), TM_R(5), TM_R(6), TM_R(7), TM_R(8), TM_R(9), TM_R(10), TM_R(11), TM_R(12),
-          TM_R(13), TM_R(14), TM_R(15)
-        : "r"(taddr) : "memory");
+// ROWP (8, 12 or 24) consecutive fp32 columns of this thread's TMEM lane: one kernel row of the last layer (see row_pad).
+// `dep`: registers of the previous row; naming them as in/out operands keeps the compiler from sinking the issue below the
+// arithmetic on them, which would serialise "load, wait, compute" again.
+#define TM_O8(b) TM_R(b), TM_R(b + 1), TM_R(b + 2), TM_R(b + 3), TM_R(b + 4), TM_R(b + 5), TM_R(b + 6), TM_R(b + 7)
+#define TM_D8(b) "+r"(dep[b]), "+r"(dep[b + 1]), "+r"(dep[b + 2]), "+r"(dep[b + 3]), "+r"(dep[b + 4]), "+r"(dep[b + 5]), "+r"(dep[b + 6]), "+r"(dep[b + 7])
+#define TM_W8(b) TM_RW(b), TM_RW(b + 1), TM_RW(b + 2), TM_RW(b + 3), TM_RW(b + 4), TM_RW(b + 5), TM_RW(b + 6), TM_RW(b + 7)
+template <int ROWP>
+__device__ __forceinline__ void tmem_ld_row_issue(unsigned taddr, unsigned (&r)[ROWP], unsigned (&dep)[ROWP]) {
+    static_assert(ROWP == 8 || ROWP == 12 || ROWP == 24, "row loads are written for 8, 12 and 24 columns");
+    // loads of 8 (4) columns, each starting at a multiple of its width
+    if constexpr (ROWP == 24) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n" : TM_O8(0) : "r"(taddr) : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n" : TM_O8(8) : "r"(taddr + 8u) : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%32];\n"       // %8..%31: dep
+                     : TM_O8(16), TM_D8(0), TM_D8(8), TM_D8(16) : "r"(taddr + 16u) : "memory");
+    } else if constexpr (ROWP == 12) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : TM_R(0), TM_R(1), TM_R(2), TM_R(3) : "r"(taddr) : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : TM_R(4), TM_R(5), TM_R(6), TM_R(7) : "r"(taddr + 4u) : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%16];\n"                        // %4..%15: dep
+                     : TM_R(8), TM_R(9), TM_R(10), TM_R(11), TM_D8(0), "+r"(dep[8]), "+r"(dep[9]), "+r"(dep[10]), "+r"(dep[11]) : "r"(taddr + 8u) : "memory");
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n" : TM_O8(0), TM_D8(0) : "r"(taddr) : "memory");
+    }
 }
-// The same load, ordered after every use of `dep` that precedes it and before every use that follows it in program order:
-// naming `dep` as in/out operands keeps the compiler from sinking the issue below the arithmetic on `dep`, which would
-// serialise "load, wait, compute" again.
-__device__ __forceinline__ void tmem_ld16_issue_after(unsigned taddr, unsigned (&r)[16], unsigned (&dep)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n"
-        : TM_R(0), TM_R(1), TM_R(2), TM_R(3), TM_R(4), TM_R(5), TM_R(6), TM_R(7), TM_R(8), TM_R(9), TM_R(10), TM_R(11), TM_R(12),
-          TM_R(13), TM_R(14), TM_R(15),
-          "+r"(dep[0]), "+r"(dep[1]), "+r"(dep[2]), "+r"(dep[3]), "+r"(dep[4]), "+r"(dep[5]), "+r"(dep[6]), "+r"(dep[7]),
-          "+r"(dep[8]), "+r"(dep[9]), "+r"(dep[10]), "+r"(dep[11]), "+r"(dep[12]), "+r"(dep[13]), "+r"(dep[14]), "+r"(dep[15])
-        : "r"(taddr) : "memory");
+template <int ROWP>
+__device__ __forceinline__ void tmem_wait_row(unsigned (&r)[ROWP]) {
+    if constexpr (ROWP == 24) asm volatile("tcgen05.wait::ld.sync.aligned;\n" : TM_W8(0), TM_W8(8), TM_W8(16) :: "memory");
+    else if constexpr (ROWP == 12) asm volatile("tcgen05.wait::ld.sync.aligned;\n" : TM_W8(0), TM_RW(8), TM_RW(9), TM_RW(10), TM_RW(11) :: "memory");
+    else asm volatile("tcgen05.wait::ld.sync.aligned;\n" : TM_W8(0) :: "memory");
 }
-__device__ __forceinline__ void tmem_wait16(unsigned (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-        : TM_RW(0), TM_RW(1), TM_RW(2), TM_RW(3), TM_RW(4), TM_RW(5), TM_RW(6), TM_RW(7), TM_RW(8), TM_RW(9), TM_RW(10), TM_RW(11),
-          TM_RW(12), TM_RW(13), TM_RW(14), TM_RW(15)
-        :: "memory");
-}
+#undef TM_O8
+#undef TM_D8
+#undef TM_W8
 #undef TM_R
 #undef TM_RW
 
@@ -198,92 +206,97 @@ __device__ __forceinline__ void store_a_chunks(unsigned char *sA, int row, int c
         *reinterpret_cast<uint4 *>(sA + a_chunk_off(row, col + 8 * g)) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
 }
 
-// Last layer, one 16-column piece [col0, col0 + 16) of this thread's half row of the accumulator: relu(acc + bias) rounded to
-// fp16.  PASS 0 adds it to the kernel-row sums, PASS 1 (the accumulator is read a second time: TMEM loads are cheap, a
-// hundred live registers are not) divides and stages the result at its final position; RIGHT: the warp's rows are right
-// kernels (rows 64..127 of a tile), whose columns are flipped inside every kernel row.  The position of the piece is a
-// run-time value on purpose: unrolling the row over compile-time columns (every address an immediate) made 12 k instructions
-// of straight-line code per kernel, four times the instruction cache, and the tail ran at the speed of instruction fetch.
+// The last layer is packed with every kernel row padded to row_pad(KS) columns (sdirt_mlp_fused_pack_layer: output
+// u * KS + w sits in accumulator column u * ROWP + w, the padding has zero weights), so the tail below loops over kernel
+// rows at RUN time while every column inside a row -- where a row sum ends, which staged element a value goes to, flipped
+// or not -- is a COMPILE-time position.  (A tail unrolled over all 441 compile-time columns was 12 k instructions of
+// straight-line code per kernel, four times the instruction cache, and ran at the speed of instruction fetch; one indexed at
+// run time paid ~12 integer instructions and two branches per element.)
+__host__ __device__ constexpr int row_pad(int ks) { return (ks + 3) / 4 * 4; }
+
 struct TailState {
-    float part, rs, rs_x, den, rc;      // total of finished kernel rows, running row, the straddling row's piece; denominator
+    float part, den, rc;                // sum of this thread's rounded kernel-row sums; the kernel's denominator, its reciprocal
     __half *dst;                        // this row of the staged block
-    const float *bl;                    // last layer's bias (SB: in shared memory)
+    const float *bl;                    // last layer's bias, padded like the accumulator (SB: in shared memory)
     unsigned lane_addr;
-    int c_lo, c_end;                    // this thread's live columns
 };
-template <int KS>
-__device__ __forceinline__ int wrap_ks(int w) {              // w mod KS for w < KS + 16
+// One kernel row u of tile row t: relu(acc + bias) rounded to fp16, two columns per FADD2 / F2FP / HMNMX2.
+// PASS 0: add the row's sum, rounded to fp16 (torch's sum(-1) of a half tensor), to st.part.
+// PASS 1 (the accumulator is read a second time: TMEM loads are cheap, two hundred live registers are not): the IEEE quotient
+// by the denominator, staged at its final position -- RIGHT: rows 64..127 of a tile are right kernels, whose columns are
+// flipped inside every kernel row -- with 32-bit stores where the staged row allows (ALIGNED: it starts on a word).
+template <int KS, int PASS, int RIGHT, int ALIGNED, bool SB>
+__device__ __forceinline__ void tail_row(const int u, const unsigned (&cur)[row_pad(KS)], TailState &st) {
+    constexpr int ROWP = row_pad(KS), NP = (KS + 1) / 2;
+    float4 bv[ROWP / 4];
 #pragma unroll
-    for (int k = 0; k < (16 + KS - 1) / KS; ++k) w = w >= KS ? w - KS : w;
-    return w;
-}
-template <int KS, int PASS, int RIGHT, bool SB>
-__device__ __forceinline__ void tail_piece(const int col0, const int w0 /* col0 mod KS */, const unsigned (&cur)[16], TailState &st) {
-    constexpr int KK = KS * KS, KC = (KK + 31) / 32, HC = (KC + 1) / 2, SPLIT = 32 * HC;
-    constexpr int U_X = (SPLIT < KK) ? SPLIT / KS : -1;
-    constexpr bool STRADDLE = U_X >= 0 && (SPLIT % KS) != 0;
-    float4 bv[4];                                             // this piece's biases (the padded bias row covers every piece)
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const float4 *bp = reinterpret_cast<const float4 *>(st.bl + col0) + g;
+    for (int g = 0; g < ROWP / 4; ++g) {
+        const float4 *bp = reinterpret_cast<const float4 *>(st.bl + u * ROWP) + g;
         bv[g] = SB ? lds_f4_here(bp) : ldg_f4_here(bp);
     }
+    float v[2 * NP];
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-        const int c0 = col0 + i;                              // even: col0 is a multiple of 16
-        const bool live0 = c0 < st.c_end, live1 = c0 + 1 < st.c_end;
+    for (int j = 0; j < NP; ++j) {
+        const int i = 2 * j;
         const float b0 = (i & 2) ? bv[i >> 2].z : bv[i >> 2].x, b1 = (i & 2) ? bv[i >> 2].w : bv[i >> 2].y;
-        // relu(round_fp16(acc + bias)) for two columns at once
         const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), make_float2(b0, b1));
         const __half2 h = __hmax2(__floats2half2_rn(s2.x, s2.y), __float2half2_rn(0.0f));
-        const float v0 = live0 ? __low2float(h) : 0.0f, v1 = live1 ? __high2float(h) : 0.0f;
-        const int wa = wrap_ks<KS>(w0 + i), wb = wrap_ks<KS>(w0 + i + 1);       // positions inside their kernel rows
-        if (PASS == 0) {
+        v[i] = __low2float(h);
+        v[i + 1] = __high2float(h);       // column KS of an odd-sized row is padding: exactly 0 (zero weights, zero bias)
+    }
+    if (PASS == 0) {
+        float rs = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int c = c0 + k;
-                st.rs += k ? v1 : v0;
-                // end of a kernel row (or of this thread's piece of the straddling row); warp-uniform
-                if ((k ? live1 : live0) && ((k ? wb : wa) == KS - 1 || c + 1 == st.c_end)) {
-                    if (STRADDLE && c >= U_X * KS && c < (U_X + 1) * KS) st.rs_x = st.rs;
-                    else st.part += __half2float(__float2half_rn(st.rs));
-                    st.rs = 0.0f;
-                }
-            }
-        } else {
-            // IEEE v / den from the refined reciprocal (div_rn's sequence); den = rc = 0 for an all-zero kernel -> 0
-            const float2 rc2 = make_float2(st.rc, st.rc), v2 = make_float2(v0, v1);
+        for (int w = 0; w < KS; ++w) rs += v[w];
+        st.part += __half2float(__float2half_rn(rs));
+    } else {
+        // IEEE v / den from the refined reciprocal (div_rn's sequence); den = rc = 0 for an all-zero kernel -> 0
+        const float2 rc2 = make_float2(st.rc, st.rc), nd2 = make_float2(-st.den, -st.den);
+        float r[2 * NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const float2 v2 = make_float2(v[2 * j], v[2 * j + 1]);
             const float2 q = __fmul2_rn(v2, rc2);
-            const float2 r = __ffma2_rn(rc2, __ffma2_rn(make_float2(-st.den, -st.den), q, v2), q);
-            if (!RIGHT) {                                     // left rows start 4-byte aligned: one 32-bit store per pair
-                if (live1) *reinterpret_cast<__half2 *>(st.dst + c0) = __floats2half2_rn(r.x, r.y);
-                else if (live0) st.dst[c0] = __float2half_rn(r.x);
-            } else {                                          // column w of a kernel row goes to KS - 1 - w
-                if (live0) st.dst[c0 + (KS - 1) - 2 * wa] = __float2half_rn(r.x);
-                if (live1) st.dst[c0 + 1 + (KS - 1) - 2 * wb] = __float2half_rn(r.y);
-            }
+            const float2 o = __ffma2_rn(rc2, __ffma2_rn(nd2, q, v2), q);
+            r[2 * j] = o.x;
+            r[2 * j + 1] = o.y;
         }
+        __half *d = st.dst + u * KS;
+        // staged position p holds column p (left) or KS - 1 - p (right)
+#define SDIRT_TAIL_OUT(p) (RIGHT ? r[KS - 1 - (p)] : r[(p)])
+        if (ALIGNED) {
+#pragma unroll
+            for (int pp = 0; pp + 1 < KS; pp += 2) *reinterpret_cast<__half2 *>(d + pp) = __floats2half2_rn(SDIRT_TAIL_OUT(pp), SDIRT_TAIL_OUT(pp + 1));
+            if (KS & 1) d[KS - 1] = __float2half_rn(SDIRT_TAIL_OUT(KS - 1));
+        } else {
+            d[0] = __float2half_rn(SDIRT_TAIL_OUT(0));
+#pragma unroll
+            for (int pp = 1; pp + 1 < KS; pp += 2) *reinterpret_cast<__half2 *>(d + pp) = __floats2half2_rn(SDIRT_TAIL_OUT(pp), SDIRT_TAIL_OUT(pp + 1));
+            if (!(KS & 1)) d[KS - 1] = __float2half_rn(SDIRT_TAIL_OUT(KS - 1));
+        }
+#undef SDIRT_TAIL_OUT
     }
 }
-// One pass over this thread's half row: 2 * HC pieces, the next one in flight while the current one is used (the two
-// register arrays alternate, so an iteration handles two pieces); the loop is NOT unrolled (see tail_piece).
+// Kernel rows [u_lo, u_hi) of this thread's tile row: the next row's accumulator is in flight while the current one is used
+// (two register arrays alternate, so an iteration handles two kernel rows); NOT unrolled.  A staged row starts at half
+// (2 * px + RIGHT) * KS * KS + u * KS: on a word boundary when RIGHT + u is even (KS odd; the host refuses even KS).
 template <int KS, int PASS, int RIGHT, bool SB>
-__device__ __forceinline__ void tail_pass(TailState &st) {
-    constexpr int KK = KS * KS, KC = (KK + 31) / 32, HC = (KC + 1) / 2;
-    unsigned ra[16], rb[16];
-    int w = st.c_lo % KS;
-    tmem_ld16_issue(st.lane_addr + (unsigned)st.c_lo, ra);
+__device__ __forceinline__ void tail_pass(const int u_lo, const int u_hi, TailState &st) {
+    constexpr int ROWP = row_pad(KS);
+    unsigned ra[ROWP], rb[ROWP];
+#pragma unroll
+    for (int i = 0; i < ROWP; ++i) rb[i] = 0u;
+    tmem_ld_row_issue<ROWP>(st.lane_addr + (unsigned)(u_lo * ROWP), ra, rb);
 #pragma unroll 1
-    for (int pc = 0; pc < HC; ++pc) {
-        const int col0 = st.c_lo + 32 * pc;
-        tmem_wait16(ra);
-        tmem_ld16_issue_after(st.lane_addr + (unsigned)(col0 + 16), rb, ra);
-        tail_piece<KS, PASS, RIGHT, SB>(col0, w, ra, st);
-        w = wrap_ks<KS>(w + 16);
-        tmem_wait16(rb);
-        if (pc + 1 < HC) tmem_ld16_issue_after(st.lane_addr + (unsigned)(col0 + 32), ra, rb);
-        tail_piece<KS, PASS, RIGHT, SB>(col0 + 16, w, rb, st);
-        w = wrap_ks<KS>(w + 16);
+    for (int u = u_lo; u < u_hi; u += 2) {
+        tmem_wait_row<ROWP>(ra);
+        if (u + 1 < u_hi) tmem_ld_row_issue<ROWP>(st.lane_addr + (unsigned)((u + 1) * ROWP), rb, ra);
+        if ((RIGHT + u) & 1) tail_row<KS, PASS, RIGHT, 0, SB>(u, ra, st); else tail_row<KS, PASS, RIGHT, 1, SB>(u, ra, st);
+        if (u + 1 < u_hi) {
+            tmem_wait_row<ROWP>(rb);
+            if (u + 2 < u_hi) tmem_ld_row_issue<ROWP>(st.lane_addr + (unsigned)((u + 2) * ROWP), ra, rb);
+            if ((RIGHT + u + 1) & 1) tail_row<KS, PASS, RIGHT, 0, SB>(u + 1, rb, st); else tail_row<KS, PASS, RIGHT, 1, SB>(u + 1, rb, st);
+        }
     }
 }
 
@@ -306,7 +319,6 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
     constexpr int STAGES = CF::STAGES, STAGE_BYTES = CF::STAGE_BYTES;
     constexpr bool SB = NCTA == 2;                           // biases resident in shared memory
     constexpr int KK = KS * KS;
-    constexpr int KC = (KK + 31) / 32;                       // 32-column chunks of the last layer
     unsigned char *sA = fm_smem;
     unsigned char *sW = fm_smem + CF::OFF_W;
     float *sBias = reinterpret_cast<float *>(fm_smem + CF::OFF_BIAS);
@@ -314,8 +326,8 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
     unsigned long long *full = reinterpret_cast<unsigned long long *>(fm_smem + CF::OFF_BAR), *empty = full + STAGES;
     unsigned long long *a_lo = empty + STAGES, *a_hi = a_lo + 1, *acc_ready = a_hi + 1;     // acc_ready[2]: one per accumulator half
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(acc_ready + 2);
-    float *s_part = reinterpret_cast<float *>(sA + TM * KK * 2);                     // [4][TM] partial sums of the last layer, behind the packed block
-    static_assert(TM * KK * 2 + 4 * TM * 4 <= A_BYTES, "the packed block and its partial sums must fit in the activation tile");
+    float *s_part = reinterpret_cast<float *>(sA + TM * KK * 2);                     // [2][TM] partial sums of the last layer, behind the packed block
+    static_assert((KS & 1) == 1 && TM * KK * 2 + 2 * TM * 4 <= A_BYTES, "the packed block and its partial sums must fit in the activation tile");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = net.n_layers;
     const unsigned n_rows = 2u * (unsigned)nb * (unsigned)nrw * (unsigned)W;
@@ -550,15 +562,10 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
             }
             // last layer: torch's fp16 sums (sum(-1) rounds every kernel row, the second sum(-1) rounds the total), then the
             // normalised kernels, the right rows flipped along their last axis, staged as the packed [64, 2, KS, KS] block.
-            // The two warps of a row split the columns in the middle ([0, SPLIT) and [SPLIT, 32 * KC)); a thread keeps its
-            // half of the row in registers (fp16 pairs) from the accumulator to the staged block.  Kernel-row sums are taken in
-            // column order; the one kernel row that straddles SPLIT is merged from two partial sums, and the totals of the two
-            // halves are added through shared memory (fp32 sums of a few fp16 values: exact, whatever the order).
+            // The two warps of a tile row split the kernel rows ([0, U_SPLIT) and [U_SPLIT, KS)); their partial totals are added
+            // through shared memory (fp32 sums of a few fp16 values: exact, whatever the order).
             {
-                constexpr int HC = (KC + 1) / 2;              // 32-column chunks per thread
-                constexpr int SPLIT = 32 * HC;                // first column of the second warp
-                constexpr int U_X = (SPLIT < KK) ? SPLIT / KS : -1;                 // kernel row that straddles SPLIT ...
-                constexpr bool STRADDLE = U_X >= 0 && (SPLIT % KS) != 0;            // ... unless SPLIT is a row boundary
+                constexpr int U_SPLIT = (KS + 1) / 2;
                 const float *bl = (SB ? sBias : bias) + net.b_off[L - 1];
                 e0 = clock64();
                 mbar_wait(acc_ready, acc_ph);
@@ -567,18 +574,15 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 e_wait += clock64() - e0;
                 e0 = clock64();
                 tc_fence_after();
-                const int c_lo = grp ? SPLIT : 0;             // this thread's columns: [c_lo, c_lo + 32 * HC), live below c_end
-                const int c_end = grp ? KK : (SPLIT < KK ? SPLIT : KK);
+                const int u_lo = grp ? U_SPLIT : 0, u_hi = grp ? KS : U_SPLIT;
                 const int right = t >> 6;                     // warp-uniform: rows 64..127 are right kernels
                 __half *dst = reinterpret_cast<__half *>(sA) + (size_t)(2 * (t & 63) + right) * KK;   // staged block [64 px][2][KK]
-                TailState st{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, dst, bl, lane_addr, c_lo, c_end};
-                tail_pass<KS, 0, 0, SB>(st);
+                TailState st{0.0f, 0.0f, 0.0f, dst, bl, lane_addr};
+                tail_pass<KS, 0, 0, SB>(u_lo, u_hi, st);
                 e_p0 += clock64() - e0;
                 s_part[grp * TM + t] = st.part;
-                s_part[(2 + grp) * TM + t] = st.rs_x;
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-                float tot = s_part[t] + s_part[TM + t];
-                if (STRADDLE) tot += __half2float(__float2half_rn(s_part[2 * TM + t] + s_part[3 * TM + t]));
+                const float tot = s_part[t] + s_part[TM + t];
                 st.den = __half2float(__float2half_rn(tot));
                 st.den = __half2float(__float2half_rn(st.den + 1e-9f));
                 if (st.den > 0.0f && st.den <= 65504.0f) {
@@ -588,7 +592,7 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                     st.den = 0.0f;                            // all-zero kernel: every quotient becomes 0
                     st.rc = 0.0f;
                 }
-                if (right) tail_pass<KS, 1, 1, SB>(st); else tail_pass<KS, 1, 0, SB>(st);
+                if (right) tail_pass<KS, 1, 1, SB>(u_lo, u_hi, st); else tail_pass<KS, 1, 0, SB>(u_lo, u_hi, st);
                 e1 = clock64();
                 tc_fence_before();
                 fence_proxy_async();
@@ -620,9 +624,17 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
 
 // Weights of one layer [n_true, K] fp16 row-major -> the layer's pre-swizzled tiles: for each half of <= 256 output rows and
 // each 64-wide k-block, rows of 128 bytes whose 16-byte chunk c sits at position c ^ (row & 7) (Swizzle<3,4,3>, the
-// shared-memory image of a K-major SWIZZLE_128B operand).  Rows >= n_true (padding) are zero.  One thread per chunk.
+// shared-memory image of a K-major SWIZZLE_128B operand).  ks > 0 (the last layer): packed row u * rowp + w takes output
+// u * ks + w (kernel rows padded to rowp columns, see row_pad).  Rows without a source (padding) are zero.  One thread per chunk.
+__device__ __forceinline__ int packed_row_source(int n, int n_true, int ks, int rowp) {
+    if (ks > 0) {
+        const int u = n / rowp, w = n - u * rowp;
+        return (u < ks && w < ks) ? u * ks + w : -1;
+    }
+    return n < n_true ? n : -1;
+}
 __global__ void __launch_bounds__(256)
-swizzle_weights_kernel(const __half *__restrict__ w, int n_true, int n_pad, int K, unsigned char *__restrict__ out) {
+swizzle_weights_kernel(const __half *__restrict__ w, int n_true, int n_pad, int K, int ks, int rowp, unsigned char *__restrict__ out) {
     const int nkb = K >> 6;
     const int64_t chunks = (int64_t)n_pad * nkb * 8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (int64_t)gridDim.x * blockDim.x) {
@@ -633,15 +645,17 @@ swizzle_weights_kernel(const __half *__restrict__ w, int n_true, int n_pad, int 
         int h, kb, r;
         if (rest < half0) { h = 0; kb = (int)(rest / rows0); r = (int)(rest - (int64_t)kb * rows0); }
         else { rest -= half0; h = 1; kb = (int)(rest / rows1); r = (int)(rest - (int64_t)kb * rows1); }
-        const int n = h * 256 + r, c = pch ^ (r & 7);
+        const int n = packed_row_source(h * 256 + r, n_true, ks, rowp), c = pch ^ (r & 7);
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (n < n_true) v = *reinterpret_cast<const uint4 *>(w + (int64_t)n * K + kb * 64 + c * 8);
+        if (n >= 0) v = *reinterpret_cast<const uint4 *>(w + (int64_t)n * K + kb * 64 + c * 8);
         *reinterpret_cast<uint4 *>(out + i * 16) = v;
     }
 }
 
-__global__ void pad_bias_kernel(const __half *__restrict__ b, int n_true, int n_pad, float *__restrict__ out) {
+__global__ void pad_bias_kernel(const __half *__restrict__ b, int n_true, int n_pad, int ks, int rowp, float *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_pad) out[i] = i < n_true ? __half2float(b[i]) : 0.0f;
+    if (i >= n_pad) return;
+    const int n = packed_row_source(i, n_true, ks, rowp);
+    out[i] = n >= 0 ? __half2float(b[n]) : 0.0f;
 }
 }  // namespace mlpf
