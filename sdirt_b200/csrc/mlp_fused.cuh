@@ -61,28 +61,39 @@ struct Net {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// The MMA warp runs its loop with all 32 lanes (warp-uniform control flow and operands, so descriptors and addresses live in
+// uniform registers); `issue` is non-zero in the one elected lane that actually issues.  (Inside an `if (lane == 0)` region
+// the compiler wraps every UTCHMMA in an ELECT / 7 x R2UR.BROADCAST / BRA.U.ANY loop -- ~25 instructions per MMA, more than
+// the issue slots a warp that shares its scheduler with two epilogue warps gets in the 128 cycles an MMA takes.)
+__device__ __forceinline__ unsigned elect_one() {
+    unsigned p;
+    asm volatile("{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\nselp.u32 %0, 1, 0, pe;\n}" : "=r"(p));
+    return p;
+}
 // tcgen05.commit: the mbarrier is signalled once every MMA issued so far by this thread has completed; NCTA = 2: the barrier
 // at the same offset in BOTH CTAs of the pair
 template <int NCTA>
-__device__ __forceinline__ void tc_commit(unsigned long long *bar) {
+__device__ __forceinline__ void tc_commit(unsigned issue, unsigned long long *bar) {
     if constexpr (NCTA == 1)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+        asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+                     "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(smem_u32(bar)), "r"(issue) : "memory");
     else
-        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                     ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+        asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n"
+                     "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}"
+                     ::"r"(smem_u32(bar)), "h"((unsigned short)3), "r"(issue) : "memory");
 }
 template <int NCTA>
-__device__ __forceinline__ void tc_mma_f16(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc, unsigned acc) {
+__device__ __forceinline__ void tc_mma_f16(unsigned issue, unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc, unsigned acc) {
     if constexpr (NCTA == 1)
         asm volatile(
-            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+            "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 q, %5, 0;\n"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(issue) : "memory");
     else
         asm volatile(
-            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
-            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+            "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 q, %5, 0;\n"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(issue) : "memory");
 }
 // CTA pair plumbing
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -307,7 +318,7 @@ __device__ __forceinline__ void tail_pass(const int u_lo, const int u_hi, TailSt
 // Hand-over of the activation tile between layers (a_lo / a_hi): the epilogue drains accumulator half 0 (output columns
 // 0..255 = k-blocks 0..3 of the next layer) into registers while the MMAs of half 1 still read the A tile; when the layer is
 // complete it stores them and signals a_lo, and the next layer's MMAs over k-blocks 0..3 run while the epilogue converts half
-// 1 (k-blocks 4..7, signalled by a_hi).
+// 1 (k-blocks 4..7, signalled by a_hi).  a_free lets the stores of half 0 start before the layer is complete.
 template <int KS, int NCTA>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__restrict__ wsw, const float *__restrict__ bias, int bias_floats,
@@ -325,7 +336,8 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
     float4 *sW1 = reinterpret_cast<float4 *>(fm_smem + CF::OFF_W1);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(fm_smem + CF::OFF_BAR), *empty = full + STAGES;
     unsigned long long *a_lo = empty + STAGES, *a_hi = a_lo + 1, *acc_ready = a_hi + 1;     // acc_ready[2]: one per accumulator half
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(acc_ready + 2);
+    unsigned long long *a_free = acc_ready + 2;              // k-blocks 0..3 of the A tile are no longer read by this layer's MMAs
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(a_free + 1);
     float *s_part = reinterpret_cast<float *>(sA + TM * KK * 2);                     // [2][TM] partial sums of the last layer, behind the packed block
     static_assert((KS & 1) == 1 && TM * KK * 2 + 2 * TM * 4 <= A_BYTES, "the packed block and its partial sums must fit in the activation tile");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -348,6 +360,7 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
         mbar_init(a_hi, EPI_THREADS + peer);
         mbar_init(acc_ready, 1);
         mbar_init(acc_ready + 1, 1);
+        mbar_init(a_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {                                   // this warp owns the TMEM allocation (all 512 columns)
@@ -388,23 +401,25 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
             }
         }
     } else if (warp == MMA_WARP) {
-        if (lane == 0 && rank == 0) {
-            // ---- MMA issuer (NCTA = 2: for both CTAs of the pair) ---------------------------------------------------------------
+        if (rank == 0) {
+            // ---- MMA issuer (NCTA = 2: for both CTAs of the pair); all lanes run the loop, one elected lane issues --------------
+            const unsigned issue = elect_one();
             int s = 0;
             unsigned ph = 0, a_ph = 0;
             const unsigned a_base = smem_u32(sA), w_base = smem_u32(sW);
-            long long t_start = clock64(), t_full = 0, t_aready = 0, t0;
+            long long t_start = clock64(), t_full = 0, t_aready = 0, t0 = 0;
             for (unsigned g = g0; g < n_groups; g += g_step) {
                 for (int l = 0; l < L; ++l) {
                     const int nkb = net.K[l] >> 6, N = net.N[l], kb_lo = min(4, nkb);
+                    const int h_last = N > 256 ? 1 : 0, kb_free = min(min(256, N) >> 6, nkb);
                     const bool tl = dbg && blockIdx.x == 0 && g == g0 + g_step;    // timeline of this CTA's second tile group
                     long long *tlp = dbg + 148 * 8 + l * 16;
-                    t0 = clock64();
+                    if (dbg) t0 = clock64();
                     // k-blocks [0, kb_lo) of this layer's A tile are written and accumulator half 0 is drained
                     mbar_wait(a_lo, a_ph);
                     if (kb_lo == nkb) mbar_wait(a_hi, a_ph);
-                    t_aready += clock64() - t0;
-                    if (tl) { tlp[0] = t0; tlp[1] = clock64(); }
+                    if (dbg) t_aready += clock64() - t0;
+                    if (tl && issue) { tlp[0] = t0; tlp[1] = clock64(); }
                     tc_fence_after();
                     for (int h = 0; h < 2; ++h) {
                         if (h * 256 < N) {
@@ -412,31 +427,36 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                             const unsigned d_tmem = tmem + (unsigned)(h * 256);
                             for (int kb = 0; kb < nkb; ++kb) {
                                 if (h == 0 && kb == kb_lo) {  // the rest of the A tile, and accumulator half 1 drained
-                                    t0 = clock64();
+                                    if (dbg) t0 = clock64();
                                     mbar_wait(a_hi, a_ph);
-                                    t_aready += clock64() - t0;
-                                    if (tl) { tlp[2] = t0; tlp[3] = clock64(); }
+                                    if (dbg) t_aready += clock64() - t0;
+                                    if (tl && issue) { tlp[2] = t0; tlp[3] = clock64(); }
                                     tc_fence_after();
                                 }
-                                t0 = clock64();
+                                if (dbg) t0 = clock64();
                                 mbar_wait(full + s, ph);
-                                t_full += clock64() - t0;
+                                if (dbg) t_full += clock64() - t0;
                                 tc_fence_after();
+                                // operand descriptors of the four K = 16 steps of this k-block: 32 bytes apart inside the 128-byte
+                                // swizzle row, i.e. +2 in the descriptor's address field
+                                const unsigned long long a_desc = smem_desc(a_base + kb * A_KB_BYTES), b_desc = smem_desc(w_base + s * STAGE_BYTES);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)   // UMMA K = 16 fp16 = 32 bytes inside the 128-byte swizzle row
-                                    tc_mma_f16<NCTA>(d_tmem, smem_desc(a_base + kb * A_KB_BYTES + k * 32), smem_desc(w_base + s * STAGE_BYTES + k * 32),
-                                                     idesc, (unsigned)((kb | k) != 0));
-                                tc_commit<NCTA>(empty + s);   // the stage is free once these MMAs have read it
+                                for (int k = 0; k < 4; ++k)
+                                    tc_mma_f16<NCTA>(issue, d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (unsigned)((kb | k) != 0));
+                                tc_commit<NCTA>(issue, empty + s);   // the stage is free once these MMAs have read it
                                 if (++s == STAGES) { s = 0; ph ^= 1u; }
+                                // the last MMA that reads k-blocks [0, kb_free) of the A tile -- the ones the epilogue overwrites with
+                                // accumulator half 0 -- is on its way: the epilogue may store as soon as it completes
+                                if (h == h_last && kb == kb_free - 1 && l + 1 < L) tc_commit<NCTA>(issue, a_free);
                             }
                         }
-                        tc_commit<NCTA>(acc_ready + h);       // this half of the accumulator is complete (h = 1: the whole layer)
-                        if (tl) tlp[4 + h] = clock64();
+                        tc_commit<NCTA>(issue, acc_ready + h);       // this half of the accumulator is complete (h = 1: the whole layer)
+                        if (tl && issue) tlp[4 + h] = clock64();
                     }
                     a_ph ^= 1u;
                 }
             }
-            if (dbg) { dbg[blockIdx.x * 8 + 0] = clock64() - t_start; dbg[blockIdx.x * 8 + 1] = t_full; dbg[blockIdx.x * 8 + 2] = t_aready; }
+            if (dbg && issue) { dbg[blockIdx.x * 8 + 0] = clock64() - t_start; dbg[blockIdx.x * 8 + 1] = t_full; dbg[blockIdx.x * 8 + 2] = t_aready; }
         } else if (NCTA == 2 && lane == 0) {
             // ---- relay (second CTA of a pair): pass this CTA's "A tile written" and "weights landed" on to the leader's barriers,
             // in the order the leader waits for them ----
@@ -465,7 +485,7 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
         const int t = (warp & 3) * 32 + lane;                 // row of the tile = TMEM lane
         const int grp = warp >> 2;                            // which of the two warps of this lane quarter
         const unsigned lane_addr = tmem + ((unsigned)((warp & 3) * 32) << 16);
-        unsigned acc_ph = 0;
+        unsigned acc_ph = 0, free_ph = 0;
         long long e_start = clock64(), e_wait = 0, e_last = 0, e_p0 = 0, e_st = 0, e0, e1;
         for (unsigned g = g0; g < n_groups; g += g_step) {
             const unsigned tile = NCTA * g + rank;
@@ -526,12 +546,14 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                         bias_relu_pack(r, bv, held[i]);
                     }
                 }
+                // half 0 (columns 0..255 = k-blocks 0..3 of the next layer's A tile) goes to shared memory as soon as this layer's
+                // MMAs have finished with those k-blocks, while the MMAs over k-blocks 4..7 of half 1 still run: the next layer
+                // starts the moment this one ends
                 e0 = clock64();
-                mbar_wait(acc_ready + 1, acc_ph);
+                mbar_wait(a_free, free_ph);
+                free_ph ^= 1u;
                 e_wait += clock64() - e0;
                 if (tl) { tlp[2] = e0; tlp[3] = clock64(); }
-                acc_ph ^= 1u;
-                tc_fence_after();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = 2 * i + grp;
@@ -541,6 +563,12 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 tc_fence_before();
                 mbar_arrive(a_lo);
                 if (tl) tlp[4] = clock64();
+                e0 = clock64();
+                mbar_wait(acc_ready + 1, acc_ph);
+                e_wait += clock64() - e0;
+                if (tl) tlp[6] = clock64();
+                acc_ph ^= 1u;
+                tc_fence_after();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = 2 * i + grp;

@@ -72,7 +72,7 @@ def main():
         print("timeline of CTA 0, second tile group (cycles from the first a_lo wait; MMA thread | epilogue thread 0):")
         for l in range(10):
             r = tl[l] - t00
-            print(f"  layer {l}: MMA wait a_lo {r[0]}..{r[1]}, wait a_hi {r[2]}..{r[3]}, issued h0 {r[4]}, h1 {r[5]} | epi wait acc0 {r[8]}..{r[9]}, E0 done/wait acc1 {r[10]}..{r[11]}, a_lo arrive {r[12]}, a_hi arrive {r[13]}")
+            print(f"  layer {l}: MMA wait a_lo {r[0]}..{r[1]}, wait a_hi {r[2]}..{r[3]}, issued h0 {r[4]}, h1 {r[5]} | epi wait acc0 {r[8]}..{r[9]}, E0 done/wait a_free {r[10]}..{r[11]}, a_lo arrive {r[12]}, acc1 {r[14]}, a_hi arrive {r[13]}")
         print(f"fused {t_f * 1e3:.0f} us = {flop / t_f / 1e9:.0f} TFLOP/s; cuBLAS route {t_c * 1e3:.0f} us = {flop / t_c / 1e9:.0f} TFLOP/s", flush=True)
 
 
