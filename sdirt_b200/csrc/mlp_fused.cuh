@@ -294,6 +294,7 @@ __device__ __forceinline__ void tail_row(const int u, const unsigned (&cur)[row_
 template <int KS, int PASS, int RIGHT, bool SB>
 __device__ __forceinline__ void tail_pass(const int u_lo, const int u_hi, TailState &st) {
     constexpr int ROWP = row_pad(KS);
+    if (u_lo >= u_hi) return;
     unsigned ra[ROWP], rb[ROWP];
 #pragma unroll
     for (int i = 0; i < ROWP; ++i) rb[i] = 0u;
@@ -487,33 +488,44 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
         const unsigned lane_addr = tmem + ((unsigned)((warp & 3) * 32) << 16);
         unsigned acc_ph = 0, free_ph = 0;
         long long e_start = clock64(), e_wait = 0, e_last = 0, e_p0 = 0, e_st = 0, e0, e1;
-        for (unsigned g = g0; g < n_groups; g += g_step) {
-            const unsigned tile = NCTA * g + rank;
-            // first Linear (K = 3) + ReLU for this row, straight into the swizzled A tile (mlp_input_layer_kernel's arithmetic);
-            // the two warps of a row take alternate groups of 8 columns
-            {
-                // tile row t: pixel (t & 63) of the tile's 64, left kernel for t < 64, right kernel for t >= 64 (a warp is
-                // all-left or all-right: the flip of the right kernels is then a compile-time address pattern)
-                const unsigned side = (unsigned)t >> 6;
-                const unsigned p = min(tile * (TM / 2) + ((unsigned)t & 63u), (n_rows >> 1) - 1);
-                const unsigned q = p / (unsigned)W, x = p - q * (unsigned)W;
-                const unsigned bq = q / (unsigned)nrw;
-                const int y = row0 + (int)(q - bq * (unsigned)nrw), b = b0 + (int)bq;
-                const float xr = __ldg(xs + x);
-                const float xv = __half2float(__float2half_rn(side ? -xr : xr));
-                const float yv = __half2float(__float2half_rn(__ldg(ys + y)));
-                const float zv = __half2float(__float2half_rn(__ldg(z + ((int64_t)b * H + y) * W + x)));
-                for (int c = 8 * grp; c < net.n1; c += 16) {
-                    unsigned o[4];
+        // first Linear (K = 3) + ReLU of tile row t (mlp_input_layer_kernel's arithmetic) into registers: tile row t is pixel
+        // (t & 63) of the tile's 64, left kernel for t < 64, right kernel for t >= 64 (a warp is all-left or all-right).  Computed
+        // one tile ahead -- while the epilogue warps wait for the last layer's accumulators -- so that the coordinate loads and
+        // the arithmetic are off the path between two tiles.
+        unsigned fl[MAX_N1 / 16][4];
+        auto first_layer = [&](unsigned tile) {
+            const unsigned side = (unsigned)t >> 6;
+            const unsigned p = min(tile * (TM / 2) + ((unsigned)t & 63u), (n_rows >> 1) - 1);
+            const unsigned q = p / (unsigned)W, x = p - q * (unsigned)W;
+            const unsigned bq = q / (unsigned)nrw;
+            const int y = row0 + (int)(q - bq * (unsigned)nrw), b = b0 + (int)bq;
+            const float xr = __ldg(xs + x);
+            const float xv = __half2float(__float2half_rn(side ? -xr : xr));
+            const float yv = __half2float(__float2half_rn(__ldg(ys + y)));
+            const float zv = __half2float(__float2half_rn(__ldg(z + ((int64_t)b * H + y) * W + x)));
+#pragma unroll
+            for (int j = 0; j < MAX_N1 / 16; ++j) {
+                const int c = 8 * grp + 16 * j;
+                if (c < net.n1) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const float4 wa = sW1[c + 2 * k], wb = sW1[c + 2 * k + 1];
                         const float va = fmaf(zv, wa.z, fmaf(yv, wa.y, xv * wa.x)) + wa.w;
                         const float vb = fmaf(zv, wb.z, fmaf(yv, wb.y, xv * wb.x)) + wb.w;
-                        o[k] = pack_relu_h2(va, vb);
+                        fl[j][k] = pack_relu_h2(va, vb);
                     }
-                    *reinterpret_cast<uint4 *>(sA + a_chunk_off(t, c)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
+            }
+        };
+        first_layer(NCTA * g0 + rank);
+        for (unsigned g = g0; g < n_groups; g += g_step) {
+            const unsigned tile = NCTA * g + rank;
+            // first Linear + ReLU of this row (computed ahead, see first_layer below) -> the swizzled A tile; the two warps of a row
+            // take alternate groups of 8 columns
+#pragma unroll
+            for (int j = 0; j < MAX_N1 / 16; ++j) {
+                const int c = 8 * grp + 16 * j;
+                if (c < net.n1) *reinterpret_cast<uint4 *>(sA + a_chunk_off(t, c)) = make_uint4(fl[j][0], fl[j][1], fl[j][2], fl[j][3]);
             }
             fence_proxy_async();
             tc_fence_before();
@@ -549,6 +561,10 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                 // half 0 (columns 0..255 = k-blocks 0..3 of the next layer's A tile) goes to shared memory as soon as this layer's
                 // MMAs have finished with those k-blocks, while the MMAs over k-blocks 4..7 of half 1 still run: the next layer
                 // starts the moment this one ends
+                if (l == 0) {                                 // the previous tile's staged block has left shared memory
+                    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                }
                 e0 = clock64();
                 mbar_wait(a_free, free_ph);
                 free_ph ^= 1u;
@@ -594,20 +610,35 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
             // through shared memory (fp32 sums of a few fp16 values: exact, whatever the order).
             {
                 constexpr int U_SPLIT = (KS + 1) / 2;
+                constexpr int U_H0 = (256 / row_pad(KS)) < KS ? (256 / row_pad(KS)) : KS;     // kernel rows that lie in accumulator half 0
                 const float *bl = (SB ? sBias : bias) + net.b_off[L - 1];
+                if (g + g_step < n_groups) first_layer(NCTA * (g + g_step) + rank);
+                const int right = t >> 6;                     // warp-uniform: rows 64..127 are right kernels
+                __half *dst = reinterpret_cast<__half *>(sA) + (size_t)(2 * (t & 63) + right) * KK;   // staged block [64 px][2][KK]
+                TailState st{0.0f, 0.0f, 0.0f, dst, bl, lane_addr};
+                const bool tl = dbg && blockIdx.x == 0 && threadIdx.x == 0 && g == g0 + g_step;
+                long long *tlp = dbg + 148 * 8 + (L - 1) * 16 + 8;         // tail timeline: 8 stamps
                 e0 = clock64();
                 mbar_wait(acc_ready, acc_ph);
+                e_wait += clock64() - e0;
+                e0 = clock64();
+                if (tl) tlp[0] = e0;
+                tc_fence_after();
+                // row sums of the kernel rows in half 0, while the MMAs of half 1 run
+                tail_pass<KS, 0, 0, SB>(grp ? U_H0 / 2 : 0, grp ? U_H0 : U_H0 / 2, st);
+                e_p0 += clock64() - e0;
+                e0 = clock64();
+                if (tl) tlp[1] = e0;
                 mbar_wait(acc_ready + 1, acc_ph);
                 acc_ph ^= 1u;
                 e_wait += clock64() - e0;
                 e0 = clock64();
+                if (tl) tlp[2] = e0;
                 tc_fence_after();
+                tail_pass<KS, 0, 0, SB>(grp ? U_H0 + (KS - U_H0 + 1) / 2 : U_H0, grp ? KS : U_H0 + (KS - U_H0 + 1) / 2, st);
                 const int u_lo = grp ? U_SPLIT : 0, u_hi = grp ? KS : U_SPLIT;
-                const int right = t >> 6;                     // warp-uniform: rows 64..127 are right kernels
-                __half *dst = reinterpret_cast<__half *>(sA) + (size_t)(2 * (t & 63) + right) * KK;   // staged block [64 px][2][KK]
-                TailState st{0.0f, 0.0f, 0.0f, dst, bl, lane_addr};
-                tail_pass<KS, 0, 0, SB>(u_lo, u_hi, st);
                 e_p0 += clock64() - e0;
+                if (tl) tlp[3] = clock64();
                 s_part[grp * TM + t] = st.part;
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 const float tot = s_part[t] + s_part[TM + t];
@@ -620,24 +651,39 @@ mlp_fused_pred_kernel(const __grid_constant__ Net net, const unsigned char *__re
                     st.den = 0.0f;                            // all-zero kernel: every quotient becomes 0
                     st.rc = 0.0f;
                 }
+                if (L == 1) {                                 // no hidden layer has waited for the previous staged block to leave
+                    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                }
+                if (tl) tlp[4] = clock64();
                 if (right) tail_pass<KS, 1, 1, SB>(u_lo, u_hi, st); else tail_pass<KS, 1, 0, SB>(u_lo, u_hi, st);
                 e1 = clock64();
+                if (tl) tlp[5] = e1;
                 tc_fence_before();
                 fence_proxy_async();
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                if (tl) tlp[6] = clock64();
+                // The staged block leaves as two bulk stores: the part under k-blocks 0 and 1 of the A tile -- which the next tile's
+                // first layer overwrites at once -- and the rest, which is only waited for before the first hidden layer's stores.
+                // (All CTAs reach this point together: 148 x 113 KB in one burst takes the memory system ~4 k cycles.)
                 if (threadIdx.x == 0 && tile < n_tiles) {
                     const unsigned rows_here = min((unsigned)TM, n_rows - tile * TM);
-                    const unsigned bytes = rows_here * (unsigned)(KK * 2);
-                    __half *gp = psf + (size_t)tile * TM * KK;
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gp), "r"(smem_u32(sA)), "r"(bytes) : "memory");
+                    const unsigned bytes = rows_here * (unsigned)(KK * 2), head = min(bytes, (unsigned)(2 * A_KB_BYTES));
+                    unsigned char *gp = reinterpret_cast<unsigned char *>(psf + (size_t)tile * TM * KK);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gp), "r"(smem_u32(sA)), "r"(head) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (bytes > head)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gp + head), "r"(smem_u32(sA) + head), "r"(bytes - head) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                if (tl) tlp[7] = clock64();
                 e_last += clock64() - e0;
                 e_st += clock64() - e1;
             }
         }
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the last staged block has been written
         if (dbg && threadIdx.x == 0) { dbg[blockIdx.x * 8 + 3] = clock64() - e_start; dbg[blockIdx.x * 8 + 4] = e_wait; dbg[blockIdx.x * 8 + 5] = e_last; dbg[blockIdx.x * 8 + 6] = e_p0; dbg[blockIdx.x * 8 + 7] = e_st; }
     }
     tc_fence_before();

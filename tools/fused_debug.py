@@ -73,6 +73,8 @@ def main():
         for l in range(10):
             r = tl[l] - t00
             print(f"  layer {l}: MMA wait a_lo {r[0]}..{r[1]}, wait a_hi {r[2]}..{r[3]}, issued h0 {r[4]}, h1 {r[5]} | epi wait acc0 {r[8]}..{r[9]}, E0 done/wait a_free {r[10]}..{r[11]}, a_lo arrive {r[12]}, acc1 {r[14]}, a_hi arrive {r[13]}")
+        r = tl[9, 8:16] - t00
+        print(f"  tail: acc0 {r[0]}, pass 0 (half-0 rows) done {r[1]}, acc1 {r[2]}, pass 0 done {r[3]}, sums exchanged {r[4]}, pass 1 done {r[5]}, staged (barrier) {r[6]}, bulk store read {r[7]}")
         print(f"fused {t_f * 1e3:.0f} us = {flop / t_f / 1e9:.0f} TFLOP/s; cuBLAS route {t_c * 1e3:.0f} us = {flop / t_c / 1e9:.0f} TFLOP/s", flush=True)
 
 
