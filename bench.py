@@ -340,21 +340,27 @@ def run_gpu(args):
               "roofline": {"bound": "hbm", "achieved": rbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                            "frac": rbytes / (ms * 1e-3) / 1e9 / hbm, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
     del psf, img
-    # BASELINE config 4 shape: PSFNet.render end to end (banded: engine kernels around the cuBLAS GEMM chain of the PSF MLP)
+    # BASELINE config 4 shape: PSFNet.render end to end (banded; the PSF MLP of a band is ONE tcgen05 kernel -- csrc/mlp_fused.cuh --
+    # the cuBLAS route is timed next to it)
     rlens = PSFNet(lens_file(LENS), sensor_res=(rh, rw), kernel_size=KS, device=dev)
     img = torch.rand((rb, 3, rh, rw), device=dev, generator=g)
     low = torch.rand((rb, 1, rh // 64 + 2, rw // 64 + 2), device=dev, generator=g)
     depth = -(torch.nn.functional.interpolate(low, size=(rh, rw), mode="bilinear", align_corners=False) * 9750 + 250)
     foc = torch.full((rb,), -1000.0, device=dev)
     ms = timed(lambda: rlens.render(img, depth, foc), 3)
+    rlens.mlp_engine = "cublas"
+    ms_cublas = timed(lambda: rlens.render(img, depth, foc), 3)
     mlp_flop_px = 2 * 2 * (3 * 128 + 128 * 512 + 8 * 512 * 512 + 512 * KS * KS)
     tpeak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1373.0))
     render_psfnet = {"metric": "pixels/s, PSFNet.render (coordinate grid -> PSF MLP both sides -> normalise -> degamma -> DP "
-                               "gather-convolution -> gamma -> clip), banded",
+                               "gather-convolution -> gamma -> clip), banded, fused tcgen05 MLP kernel",
                      "value": rb * rh * rw / (ms * 1e-3), "unit": "pixels/s", "shape": [rb, 3, rh, rw], "ks": KS,
+                     "cublas_route_pixels_per_s": rb * rh * rw / (ms_cublas * 1e-3),
                      "roofline": {"bound": "tensor", "achieved": rb * rh * rw * mlp_flop_px / (ms * 1e-3) / 1e12, "peak": tpeak,
                                   "unit": "TFLOP/s", "frac": rb * rh * rw * mlp_flop_px / (ms * 1e-3) / 1e12 / tpeak,
-                                  "note": "9.56 MFLOP/pixel of 16-bit GEMM (cuBLAS) dominate; peak = measured dense 16-bit matmul"}}
+                                  "note": "9.56 MFLOP/pixel of 16-bit MMA dominate (mlp_fused_pred_kernel, CTA pairs); the time is "
+                                          "the whole render call, convolution included; peak = measured dense 16-bit matmul "
+                                          "(MEASURED_PEAKS.json, sustained)"}}
     del img, depth, rlens
 
     # ---- CPU baseline on this box's host cores (bounded sample) --------------------------------------

@@ -187,8 +187,30 @@ class PSFNet(Lensgroup):
     # ---- banded render: the per-pixel PSF tensor only ever exists for one band of rows -------------------
     render_band_rows = 16            # rows per band (the render kernels' tile height)
     render_band_pixels = 98304       # pixels per band batch: images are grouped until a band holds about this many
-    render_overlap = True            # pack + convolve band i on a second stream while the GEMMs of band i + 1 run
-    mlp_engine = "cublas"            # "fused": the whole of `pred` for a band as one tcgen05 kernel (csrc/mlp_fused.cuh)
+    render_band_pixels_fused = 393216  # budget of the fused engine's automatic band shape (2 x 0.7 GB of fp16 PSFs in flight)
+    render_overlap = True            # pack + convolve band i on a second stream while the MLP of band i + 1 runs
+    mlp_engine = "fused"             # "fused": the whole of `pred` for a band as one tcgen05 kernel (csrc/mlp_fused.cuh);
+                                     # "cublas": input-layer kernel + torch GEMM chain + pack kernel (same results bit for bit)
+
+    def _fused_band_shape(self, N, H, W):
+        """(rows, images) of a band for the fused engine.  Its persistent kernel gives every CTA pair groups of 128 pixels, so a
+        band costs ceil(pixels / 128 / (SMs / 2)) rounds: pick the shape under the pixel budget that wastes the least of its
+        last round (98304 pixels = 10.4 rounds cost 11; 196608 = 20.8 cost 21).  Rows in multiples of the render kernels' 16."""
+        if "render_band_rows" in self.__dict__ or "render_band_pixels" in self.__dict__:      # set by hand: keep
+            rows = max(1, min(int(self.render_band_rows), H))
+            return rows, max(1, min(N, int(self.render_band_pixels) // (rows * W)))
+        slots = max(1, E.lib().sdirt_device_sm_count() // 2)
+        best = None
+        for rows in sorted({min(H, r) for r in range(16, 129, 16)}):
+            for nb in range(1, N + 1):
+                px = nb * rows * W
+                if px > max(int(self.render_band_pixels_fused), rows * W) and nb > 1:
+                    break
+                rounds = -(-px // 128) / slots
+                score = (round(rounds / -(-rounds // 1), 3), px)
+                if best is None or score > best[0]:
+                    best = (score, rows, nb)
+        return best[1], best[2]
 
     def _mlp_fused(self):
         """The MLP packed for sdirt_mlp_fused_pred, cached on the parameters' versions."""
@@ -242,8 +264,11 @@ class PSFNet(Lensgroup):
         (w1, b1), chain = self._mlp_half_layers()
         img32 = img.float().contiguous()
         rl, rr = torch.empty_like(img32), torch.empty_like(img32)
-        rows = max(1, min(int(self.render_band_rows), H))
-        nb = max(1, min(N, int(self.render_band_pixels) // (rows * W)))
+        if self.mlp_engine == "fused":
+            rows, nb = self._fused_band_shape(N, H, W)
+        else:
+            rows = max(1, min(int(self.render_band_rows), H))
+            nb = max(1, min(N, int(self.render_band_pixels) // (rows * W)))
         # Two streams: the GEMM chain of band i + 1 (tensor cores) runs while band i is packed and convolved (memory pipes).
         # raw / psf buffers are double-buffered by hand so that no tensor crosses streams through the caching allocator.
         main = torch.cuda.current_stream(img.device)

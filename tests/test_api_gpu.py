@@ -286,10 +286,17 @@ def test_render_fused_mlp_engine(golden):
     torch.manual_seed(5)
     lens = PSFNet(lens_path("rf50mm"), sensor_res=(16, 24), kernel_size=21, device=DEV)
     img, depth, foc = (torch.from_numpy(g[k]).to(DEV) for k in ("img", "depth", "foc"))
+    lens.mlp_engine = "cublas"
     base = lens.render(img, depth, foc)
-    lens.mlp_engine = "fused"
+    lens.mlp_engine = "fused"                                               # the default
     out = lens.render(img, depth, foc)
     assert np.abs(out.cpu().numpy() - g["render_out"]).max() < 2e-3
     assert (out - base).abs().max().item() < 1e-3
     lens.render_band_rows, lens.render_band_pixels = 8, 1                   # several bands, one image at a time
     assert torch.equal(lens.render(img, depth, foc), out)
+    from sdirt_b200 import _engine as E
+    try:                                                                    # single CTAs instead of CTA pairs: same bits
+        E.lib().sdirt_mlp_fused_cta_group(1)
+        assert torch.equal(lens.render(img, depth, foc), out)
+    finally:
+        E.lib().sdirt_mlp_fused_cta_group(2)

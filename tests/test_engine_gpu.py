@@ -691,3 +691,33 @@ def test_mlp_fused_other_windows_and_errors():
     with pytest.raises(RuntimeError):
         E.FusedMlp([(torch.zeros(128, 3, device=DEV), torch.zeros(128, device=DEV)), (torch.zeros(100, 128, device=DEV), torch.zeros(100, device=DEV)),
                     (torch.zeros(49, 100, device=DEV), torch.zeros(49, device=DEV))])     # hidden width 100: not a multiple of 64
+
+
+def test_mlp_fused_many_tiles_pairs_vs_single_ctas():
+    """More tile groups than CTA pairs (every barrier goes through several phases; an odd number of tiles leaves a pair's
+    second tile past the end) -- CTA pairs (cta_group::2) and single CTAs must give the same bits, equal to the cuBLAS route."""
+    from sdirt_b200 import _engine as E
+    lin = _seeded_linears()
+    fused = E.FusedMlp(lin)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    B, H, W = 3, 70, 96                                                       # 20160 pixels = 315 tiles: 158 groups for 74 pairs
+    z = torch.rand((B, H, W), device=DEV, generator=gen)
+    xs, ys = cu(O._torch_linspace(-1, 1, W)), cu(O._torch_linspace(1, -1, H))
+    try:
+        E.lib().sdirt_mlp_fused_cta_group(1)
+        one = fused.pred(xs, ys, z, 0, B, 0, H, 21)
+    finally:
+        E.lib().sdirt_mlp_fused_cta_group(2)
+    two = fused.pred(xs, ys, z, 0, B, 0, H, 21)
+    assert torch.equal(one, two)
+    w1, b1 = lin[0][0].half().contiguous(), lin[0][1].half().contiguous()
+    h = E.mlp_input_layer(xs, ys, z, 0, B, 0, H, w1, b1)
+    for i, (w, b) in enumerate(lin[1:]):
+        w16, b16 = w.half(), b.half()
+        if i == len(lin) - 2:
+            w16, b16 = torch.cat((w16, w16.new_zeros(7, w16.shape[1]))), torch.cat((b16, b16.new_zeros(7)))
+        h = torch._addmm_activation(b16.contiguous(), h, w16.contiguous().t())
+    via = E.psf_pack(h, 21)
+    assert float((two == via).float().mean()) > 0.999
+    assert (two.float() - via.float()).abs().max().item() <= 4e-3 * via.float().max().item()
+    assert not torch.isnan(two.float()).any()

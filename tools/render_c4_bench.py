@@ -37,18 +37,24 @@ def main():
     low = torch.rand((B, 1, H // 64 + 2, W // 64 + 2), device=dev, generator=g)
     depth = -(torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=False) * 9750 + 250)
     foc = torch.full((B,), -1000.0, device=dev)
+    px = B * H * W
+    flop_px = 2 * 2 * (3 * 128 + 128 * 512 + 8 * 512 * 512 + 512 * 441)          # both sides, FMA = 2
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    px = B * H * W
-    flop_px = 2 * 2 * (3 * 128 + 128 * 512 + 8 * 512 * 512 + 512 * 441)          # both sides, FMA = 2
+    lens.mlp_engine = "cublas"
+    ms_c = timed(lambda: lens.render(img, depth, foc))
+    print(f"PSFNet.render, cuBLAS route (rows={lens.render_band_rows} band_px={lens.render_band_pixels}): {ms_c:.2f} ms  {B * H * W / ms_c * 1e3:.3e} px/s  "
+          f"{B * H * W * flop_px / (ms_c * 1e-3) / 1e12:.0f} TFLOP/s")
+    lens.mlp_engine = "fused"
+    print("fused engine band shape (rows, images):", lens._fused_band_shape(B, H, W))
     l0 = E.launch_count()
     ms = timed(lambda: lens.render(img, depth, foc))
     tf = px * flop_px / (ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 0.0)) or float("nan")
-    print(f"PSFNet.render banded {B}x3x{H}x{W} ks=21 rows={lens.render_band_rows} band_px={lens.render_band_pixels} overlap={int(lens.render_overlap)}: {ms:.2f} ms  "
+    print(f"PSFNet.render banded, fused MLP kernel, {B}x3x{H}x{W} ks=21 overlap={int(lens.render_overlap)}: {ms:.2f} ms  "
           f"{px / ms * 1e3:.3e} px/s  {tf:.0f} TFLOP/s (MLP, 9.56 MFLOP/px) = {tf / peak:.3f} of measured dense 16-bit peak {peak:.0f}; "
           f"engine launches/call {(E.launch_count() - l0) // 4}; peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
     # per-stage split of one band batch
