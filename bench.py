@@ -171,10 +171,12 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU leg)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # The JSON line must be the only thing on stdout, and NCCL writes its version banner to file descriptor 1 when the first
+    # communicator is built: point fd 1 at stderr for the whole run and keep the real stdout for the one line at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # the JSON line must be the only thing on stdout: NCCL_DEBUG=VERSION (set in some images) prints a banner there
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
         # torchrun pins OMP_NUM_THREADS=1; the host side of the end-to-end path (the reference's CPU RNG + polar transform of
         # the shared sample set, optics.py:483-487) may use this rank's share of the cores
@@ -370,7 +372,7 @@ def run_gpu(args):
         cpu = {"value": rates[-1], "unit": "rays/s", "cores": cores, "kind": "port",
                "sample": "64 points x 131072 rays of depth slab 1 (oracle/dp_oracle.py, numpy, one process per core)"}
 
-    print(json.dumps({
+    line = json.dumps({
         "metric": "rays/sec traced+splatted into DP L/R PSFs", "value": value, "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -385,7 +387,9 @@ def run_gpu(args):
         "numerics_modes_rays_per_s": modes,
         "render": render,
         "render_psfnet": render_psfnet,
-    }))
+    })
+    sys.stdout.flush()
+    os.write(real_stdout, (line + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
