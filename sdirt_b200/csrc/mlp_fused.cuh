@@ -288,27 +288,30 @@ __device__ __forceinline__ void tail_row(const int u, const unsigned (&cur)[row_
 #undef SDIRT_TAIL_OUT
     }
 }
-// Kernel rows [u_lo, u_hi) of this thread's tile row: the next row's accumulator is in flight while the current one is used
-// (two register arrays alternate, so an iteration handles two kernel rows); NOT unrolled.  A staged row starts at half
+// Kernel rows [u_lo, u_hi) of this thread's tile row; NOT unrolled.  A staged row starts at half
 // (2 * px + RIGHT) * KS * KS + u * KS: on a word boundary when RIGHT + u is even (KS odd; the host refuses even KS).
 template <int KS, int PASS, int RIGHT, bool SB>
 __device__ __forceinline__ void tail_pass(const int u_lo, const int u_hi, TailState &st) {
     constexpr int ROWP = row_pad(KS);
-    if (u_lo >= u_hi) return;
     unsigned ra[ROWP], rb[ROWP];
 #pragma unroll
-    for (int i = 0; i < ROWP; ++i) rb[i] = 0u;
-    tmem_ld_row_issue<ROWP>(st.lane_addr + (unsigned)(u_lo * ROWP), ra, rb);
+    for (int i = 0; i < ROWP; ++i) ra[i] = rb[i] = 0u;
+    int u = u_lo;
+    // two kernel rows per iteration: both loads, one wait, then the two rows' arithmetic in one basic block, where the
+    // scheduler interleaves their dependency chains (a warp has one partner on its scheduler to hide latency behind)
 #pragma unroll 1
-    for (int u = u_lo; u < u_hi; u += 2) {
+    for (; u + 1 < u_hi; u += 2) {
+        tmem_ld_row_issue<ROWP>(st.lane_addr + (unsigned)(u * ROWP), ra, rb);
+        tmem_ld_row_issue<ROWP>(st.lane_addr + (unsigned)((u + 1) * ROWP), rb, ra);
         tmem_wait_row<ROWP>(ra);
-        if (u + 1 < u_hi) tmem_ld_row_issue<ROWP>(st.lane_addr + (unsigned)((u + 1) * ROWP), rb, ra);
+        tmem_wait_row<ROWP>(rb);
+        if ((RIGHT + u) & 1) { tail_row<KS, PASS, RIGHT, 0, SB>(u, ra, st); tail_row<KS, PASS, RIGHT, 1, SB>(u + 1, rb, st); }
+        else { tail_row<KS, PASS, RIGHT, 1, SB>(u, ra, st); tail_row<KS, PASS, RIGHT, 0, SB>(u + 1, rb, st); }
+    }
+    if (u < u_hi) {
+        tmem_ld_row_issue<ROWP>(st.lane_addr + (unsigned)(u * ROWP), ra, rb);
+        tmem_wait_row<ROWP>(ra);
         if ((RIGHT + u) & 1) tail_row<KS, PASS, RIGHT, 0, SB>(u, ra, st); else tail_row<KS, PASS, RIGHT, 1, SB>(u, ra, st);
-        if (u + 1 < u_hi) {
-            tmem_wait_row<ROWP>(rb);
-            if (u + 2 < u_hi) tmem_ld_row_issue<ROWP>(st.lane_addr + (unsigned)((u + 2) * ROWP), ra, rb);
-            if ((RIGHT + u + 1) & 1) tail_row<KS, PASS, RIGHT, 0, SB>(u + 1, rb, st); else tail_row<KS, PASS, RIGHT, 1, SB>(u + 1, rb, st);
-        }
     }
 }
 
