@@ -9,19 +9,21 @@
 //
 //   * the activation tile [128, K <= 512] fp16 lives in shared memory (128 KB) in the canonical K-major SWIZZLE_128B
 //     layout of a tcgen05 A operand and never leaves the SM;
-//   * the weights arrive PRE-SWIZZLED (sdirt_mlp_fused_pack_weights lays every [<= 256 x 64] tile out as its shared-memory
-//     image), so a pipeline stage is one contiguous cp.async.bulk (UBLKCP) into a 3-stage mbarrier ring: no tensor maps;
-//   * one elected thread issues tcgen05.mma (M = 128, N = 256 / 192, K = 16) into a [128 lanes x 512 columns] fp32
-//     accumulator that fills the SM's TMEM; tcgen05.commit releases ring stages and hands the accumulator over;
-//   * four epilogue warps (thread = row = TMEM lane) read it back with tcgen05.ld, add the bias, ReLU, round to fp16 and
-//     write the next layer's A operand straight into the swizzled tile; after the last layer they compute torch's two-stage
-//     fp16 sums from TMEM, normalise, flip the right rows and stage the packed [64, 2, ks, ks] block, which leaves with one
-//     bulk store;
-//   * the first Linear (K = 3) is computed by the same four warps on the CUDA cores directly into the A tile.
+//   * the weights arrive PRE-SWIZZLED (sdirt_mlp_fused_pack_layer lays every [<= 256 x 64] tile out as its shared-memory
+//     image), so a pipeline stage is one contiguous cp.async.bulk (UBLKCP) into an mbarrier ring: no tensor maps;
+//   * CTA pairs (cluster of 2): tcgen05.mma.cta_group::2 (UMMA M = 256: 128 rows from each CTA, N = 256, K = 16) into a
+//     [128 lanes x 512 columns] fp32 accumulator per CTA that fills the SM's TMEM; each CTA stages half of every weight
+//     tile; tcgen05.commit (multicast to both CTAs) releases ring stages and hands the accumulator over;
+//   * eight epilogue warps (thread = row = TMEM lane, two warps per lane quarter) read it back with tcgen05.ld, add the bias,
+//     ReLU, round to fp16 and write the next layer's A operand straight into the swizzled tile; after the last layer they
+//     compute torch's two-stage fp16 sums from TMEM, normalise, flip the right rows and stage the packed [64, 2, ks, ks]
+//     block, which leaves with two bulk stores;
+//   * the first Linear (K = 3) is computed by the same warps on the CUDA cores, one tile ahead.
 //
-// Roles: warps 0-3 epilogue / first layer, warp 4 weight producer, warp 5 MMA issuer + TMEM owner.  Persistent: CTAs loop
-// over tiles.  Numerics: identical rounding points to the cuBLAS route (fp32 accumulate, bias added in fp32, one rounding);
-// only the fp32 summation order inside a dot product differs, as it does between any two GEMM implementations.
+// Roles: warps 0-7 epilogue / first layer, warp 8 weight producer, warp 9 MMA issuer + TMEM owner.  Persistent: CTA pairs loop
+// over groups of two tiles.  Numerics: identical rounding points to the cuBLAS route (fp32 accumulate, bias added in fp32, one
+// rounding); only the fp32 summation order inside a dot product differs, as it does between any two GEMM implementations.
+// DESIGN.md 3.4 has the measurements behind each choice.
 #pragma once
 
 namespace mlpf {

@@ -199,7 +199,8 @@ class PSFNet(Lensgroup):
         if "render_band_rows" in self.__dict__ or "render_band_pixels" in self.__dict__:      # set by hand: keep
             rows = max(1, min(int(self.render_band_rows), H))
             return rows, max(1, min(N, int(self.render_band_pixels) // (rows * W)))
-        slots = max(1, E.lib().sdirt_device_sm_count() // 2)
+        sms = E.lib().sdirt_device_sm_count()
+        slots = max(1, (sms if sms > 0 else 148) // 2)
         best = None
         for rows in sorted({min(H, r) for r in range(16, 129, 16)}):
             for nb in range(1, N + 1):

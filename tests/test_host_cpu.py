@@ -127,3 +127,38 @@ def test_bench_workload_shape():
     assert p.shape == (4096, 3) and abs(float(p[0, 0]) + 127 / 128) < 1e-6 and abs(float(p[0, 1]) - 127 / 128) < 1e-6
     depths = [float(bench.bank_points(s)[0, 2]) for s in range(32)]
     assert min(depths) >= -20000 - 1e-3 and max(depths) <= -200 + 1e-3 and len(set(depths)) == 32
+
+
+def test_fused_kernel_sass_is_tcgen05_cta_pairs():
+    """The fused PSF-MLP kernel is the tcgen05 / TMEM path it claims to be: 2-CTA UMMA, multicast commits, TMEM loads, bulk
+    copies, cluster barriers (SASS mnemonics of profiles' B200 recipe); and its issue loop holds no ELECT / R2UR waterfall."""
+    import subprocess
+    from sdirt_b200 import build
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    body, on = [], False
+    for line in sass.splitlines():
+        if "Function :" in line:
+            on = "mlp_fused_pred_kernelILi21ELi2E" in line
+        elif on:
+            body.append(line)
+    text = "\n".join(body)
+    for mnemonic in ("UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "LDTM", "UBLKCP", "UCGABAR_ARV", "FADD2", "FFMA2"):
+        assert mnemonic in text, mnemonic
+    parts = text.split("UTCHMMA.2CTA")
+    n_mma = len(parts) - 1
+    assert n_mma >= 4 and n_mma % 4 == 0                         # four K = 16 steps per stage at every (cloned) issue site
+    for i in range(1, n_mma, 4):                                 # back-to-back MMAs, operands already in uniform registers
+        assert not any("R2UR" in seg or "ELECT" in seg for seg in parts[i:i + 3])
+
+
+def test_fused_band_shape_fills_rounds():
+    """PSFNet's band chooser for the fused engine: bands whose last round of the persistent kernel is (nearly) full."""
+    from sdirt_b200.deeplens.psfnet import PSFNet
+    stub = PSFNet.__new__(PSFNet)
+    for n, h, w in ((2, 1024, 1536), (4, 512, 768), (16, 1024, 1536), (1, 512, 768)):
+        rows, nb = PSFNet._fused_band_shape(stub, n, h, w)
+        assert rows % 16 == 0 and 1 <= nb <= n and rows <= h
+        rounds = -(-(nb * rows * w) // 128) / 74
+        assert rounds / -(-rounds // 1) > 0.95 and nb * rows * w <= max(PSFNet.render_band_pixels_fused, rows * w)
+    stub.render_band_rows, stub.render_band_pixels = 8, 1           # set by hand: kept
+    assert PSFNet._fused_band_shape(stub, 4, 512, 768) == (8, 1)
