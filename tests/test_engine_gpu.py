@@ -721,3 +721,38 @@ def test_mlp_fused_many_tiles_pairs_vs_single_ctas():
     assert float((two == via).float().mean()) > 0.999
     assert (two.float() - via.float()).abs().max().item() <= 4e-3 * via.float().max().item()
     assert not torch.isnan(two.float()).any()
+
+
+def test_mlp_fused_narrow_layers():
+    """Layer shapes off the flagship's: first Linear of 64, hidden widths of 256 and 128 (one accumulator half only, fewer
+    k-blocks than the hand-over splits at), ks = 7 -- against the same arithmetic through library GEMMs."""
+    from sdirt_b200 import _engine as E
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    dims = [3, 64, 256, 128, 49]
+    lin = []
+    for k, n in zip(dims[:-1], dims[1:]):
+        w = torch.randn((n, k), device=DEV, generator=gen) * (2.0 / k) ** 0.5
+        b = torch.rand((n,), device=DEV, generator=gen) * 0.1
+        lin.append((w, b))
+    fused = E.FusedMlp(lin)
+    B, H, W = 2, 24, 40
+    z = torch.rand((B, H, W), device=DEV, generator=gen)
+    xs, ys = cu(O._torch_linspace(-1, 1, W)), cu(O._torch_linspace(1, -1, H))
+    w1, b1 = lin[0][0].half().contiguous(), lin[0][1].half().contiguous()
+    h = E.mlp_input_layer(xs, ys, z, 0, B, 0, H, w1, b1)
+    for i, (w, b) in enumerate(lin[1:]):
+        w16, b16 = w.half(), b.half()
+        padn = (-w16.shape[0]) % 8
+        if padn:
+            w16, b16 = torch.cat((w16, w16.new_zeros(padn, w16.shape[1]))), torch.cat((b16, b16.new_zeros(padn)))
+        h = torch._addmm_activation(b16.contiguous(), h, w16.contiguous().t())
+    via = E.psf_pack(h, 7)
+    for ncta in (2, 1):
+        try:
+            E.lib().sdirt_mlp_fused_cta_group(ncta)
+            got = fused.pred(xs, ys, z, 0, B, 0, H, 7)
+        finally:
+            E.lib().sdirt_mlp_fused_cta_group(2)
+        assert got.shape == via.shape
+        assert float((got == via).float().mean()) > 0.99
+        assert (got.float() - via.float()).abs().max().item() <= 4e-3 * via.float().max().item()
