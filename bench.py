@@ -306,7 +306,10 @@ def run_gpu(args):
                         "12 B/point + the L2-resident 16 MB sample set and writes 7 KB/point. peak = FFMA micro-benchmark "
                         "measured in this run (MEASURED_PEAKS.json has no fp32 entry; its hbm_gbs=%s). achieved = %.0f "
                         "flop/ray (SURVEY 8d: the reference algorithm's minimal per-ray count) x rays per launch / CUDA-event "
-                        "time of the step's launches (dp_lut + bank + finalize); traffic = ncu dram bytes per launch."
+                        "time of the step's launches (dp_lut + bank + finalize); traffic = ncu dram bytes per launch. The count is "
+                        "the REFERENCE algorithm's (Newton iterations on every surface); the kernel reaches a fraction near 1 "
+                        "because it executes fewer flops per ray than that (closed-form sphere roots) and issues its FMA-pipe "
+                        "arithmetic for two rays at once (FFMA2), not because it exceeds the pipe: ncu's own pipe utilisation is in profiles/."
                         % (peaks.get("hbm_gbs"), FLOP_PER_RAY)}
 
     # ---- secondary numbers (not the contract metric): other numerics modes, and the HBM-bound render kernel --------------

@@ -267,6 +267,11 @@ int sdirt_gamma_noise_clip(float *x_dev, const float *randn_dev, const float *no
                            int N, int C2, int H, int W, void *stream);
 
 /* ---- measurement helper: dependent-free FP32 FMA loop, returns nothing; timed by the caller -------- */
+/* Testing aid: runs the packed (two rays per thread) strict first-surface step and the one-ray one on the m rays from one object
+ * point and counts, per field (o.x o.y o.z d.x d.y d.z, alive flag, rays), those whose bits differ: mismatch_dev[8], example_dev[16]. */
+int sdirt_debug_strict_pair(const sdirt_lens *lens, double wvln_um, const float *point_dev, const float *pupil_xy_dev, int64_t n_samples,
+                            double pupil_z, int *mismatch_dev, float *example_dev, void *stream);
+
 int sdirt_fp32_peak_probe(float *out_dev, int blocks, int threads, int iters, void *stream);
 
 #ifdef __cplusplus

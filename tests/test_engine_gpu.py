@@ -756,3 +756,25 @@ def test_mlp_fused_narrow_layers():
         assert got.shape == via.shape
         assert float((got == via).float().mean()) > 0.99
         assert (got.float() - via.float()).abs().max().item() <= 4e-3 * via.float().max().item()
+
+
+def test_packed_strict_first_surface_is_bit_identical():
+    """The two-rays-per-thread kernels take the strict first surface in packed fp32; every field of every ray must carry the bits
+    of the one-ray step (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 -- the products there are scalar on purpose)."""
+    import ctypes as C
+    from sdirt_b200 import _engine as E
+    lens = engine_lens("rf50mm")
+    g = torch.Generator().manual_seed(0)
+    m = 100000
+    th = torch.rand(m, generator=g) * 2 * np.pi
+    rr = torch.sqrt(torch.rand(m, generator=g) * 6.019352912902832 ** 2)
+    pup = torch.stack([rr * torch.cos(th), rr * torch.sin(th)], -1).to(DEV).contiguous()
+    lib = E.lib()
+    lib.sdirt_debug_strict_pair.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    for pt in ([-86.98888, 2320.7637, -12153.938], [-5909.853, -2731.2825, -17124.674], [3.0, 2.0, -500.0]):
+        p = torch.tensor(pt, device=DEV)
+        mm, ex = torch.zeros(8, dtype=torch.int32, device=DEV), torch.zeros(16, device=DEV)
+        assert lib.sdirt_debug_strict_pair(lens._h, 0.589, C.c_void_p(p.data_ptr()), C.c_void_p(pup.data_ptr()), m, 22.51324462890625,
+                                           C.c_void_p(mm.data_ptr()), C.c_void_p(ex.data_ptr()), None) == 0
+        torch.cuda.synchronize()
+        assert mm.tolist() == [0] * 8, (pt, mm.tolist(), ex.tolist())
