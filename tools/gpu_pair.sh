@@ -1,5 +1,4 @@
 mkdir -p gpurun_out/r01E
-timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r01E/pytest_gpu.log 2>&1; tail -3 gpurun_out/r01E/pytest_gpu.log
 QB_MODES=hybrid,adaptive,fast timeout 300 python tools/quick_bench.py rf50mm 1184 1048576 > gpurun_out/r01E/quick_rf50.log 2>&1; cat gpurun_out/r01E/quick_rf50.log
 QB_MODES=hybrid,adaptive,fast timeout 300 python tools/quick_bench.py rf35mm 1184 1048576 > gpurun_out/r01E/quick_rf35.log 2>&1; cat gpurun_out/r01E/quick_rf35.log
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/r01E/bench.json 2>/dev/null; python -c "
