@@ -26,6 +26,7 @@
  *   sdirt_mlp_input_layer           <- coordinate grid + first Linear+ReLU deeplens/psfnet.py:681-694; psfnet_arch.py:40-41
  *   sdirt_psf_pack                  <- PSFNet.pred: flip, stack, normalise deeplens/psfnet.py:326-333
  *   sdirt_mlp_fused_pred            <- PSFNet.pred (grid, MLP x2, flip, stack, normalise) deeplens/psfnet.py:317-336, 681-705; psfnet_arch.py:32-56
+ *   sdirt_tone_degamma              <- PSFNet.degamma deeplens/psfnet.py:589-603
  *   sdirt_gamma_noise_clip          <- PSFNet.gamma / noise / clip (train) deeplens/psfnet.py:605-620, 629-642, 708-713
  *
  * Conventions: every pointer marked "dev" is device memory owned by the caller (a torch CUDA tensor's
@@ -263,6 +264,10 @@ int sdirt_mlp_fused_cta_group(int ncta);
  * place on x_dev[N, 2C, H, W] (the convolved linear image, left channels first).  randn_dev: standard-normal draws of
  * that shape; noise_range_dev[N]; weight_dev[N, W]: the linspace(range1, range2, W) ramp, read mirrored for the right
  * channels.  x <- clip(gamma(x) + (randn * noise_range) * weight, 0, 1). */
+/* PSFNet.degamma (psfnet.py:589-603) elementwise, out_dev may equal in_dev: the linear image that sdirt_render_local_psf(_rows)
+ * then takes with tone bit 1 clear (same bits as the fused degamma; evaluated once per pixel instead of once per tile halo). */
+int sdirt_tone_degamma(const float *in_dev, float *out_dev, int64_t n, void *stream);
+
 int sdirt_gamma_noise_clip(float *x_dev, const float *randn_dev, const float *noise_range_dev, const float *weight_dev,
                            int N, int C2, int H, int W, void *stream);
 

@@ -83,6 +83,7 @@ def lib():
     L.sdirt_mlp_fused_cta_group.argtypes = [cint]
     L.sdirt_mlp_fused_cta_group.restype = cint
     L.sdirt_mlp_fused_pred.argtypes = [C.POINTER(MlpShape), vp, vp, vp, vp, vp, vp, vp, cint, cint, cint, cint, cint, cint, cint, cint, vp, vp]
+    L.sdirt_tone_degamma.argtypes = [vp, vp, i64, vp]
     L.sdirt_gamma_noise_clip.argtypes = [vp, vp, vp, vp, cint, cint, cint, cint, vp]
     L.sdirt_fp32_peak_probe.argtypes = [vp, cint, cint, cint, vp]
     _lib = L
@@ -294,10 +295,20 @@ def splat_rays(o, d, ra, centre, ks, pixel_size, dp=None):
     return out_l, out_r
 
 
+def tone_degamma(img, out=None):
+    """PSFNet.degamma of a float32 image (any shape), elementwise; `out` may be `img`."""
+    if out is None:
+        out = torch.empty_like(img)
+    _check(lib().sdirt_tone_degamma(_dev(img, "img"), _dev(out, "out"), img.numel(), _stream(img)))
+    return out
+
+
 def render_local_psf(img, psf, ks, tone=0):
     """img [B,C,H,W] float32, psf [B,H,W,2,ks,ks] float32/float16 -> (rl, rr) float32.
     tone bits: 1 = degamma the input, 2 = gamma + clip the output."""
     b, c, h, w = img.shape
+    if tone & 1:                       # once per pixel here instead of once per tile halo inside the kernel (same bits)
+        img, tone = tone_degamma(img), tone & ~1
     if psf.dtype not in (torch.float32, torch.float16):
         raise RuntimeError("sdirt_engine: psf must be float32 or float16")
     if psf.numel() != b * h * w * 2 * ks * ks:

@@ -264,6 +264,8 @@ class PSFNet(Lensgroup):
         ys = torch.linspace(1, -1, H).to(img.device)
         (w1, b1), chain = self._mlp_half_layers()
         img32 = img.float().contiguous()
+        if tone & 1:                                                       # degamma once per call, not per band and tile halo
+            img32, tone = E.tone_degamma(img32, out=img32 if img32.data_ptr() != img.data_ptr() else None), tone & ~1
         rl, rr = torch.empty_like(img32), torch.empty_like(img32)
         if self.mlp_engine == "fused":
             rows, nb = self._fused_band_shape(N, H, W)
