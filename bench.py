@@ -4,8 +4,10 @@
 Workload (BASELINE.json configs[1]): the rf50mm F/4 PSF bank for PSFNet fitting, 64x64 field points x 32 depths,
 2 M rays per point.  One "step" = one depth slab of that bank: 4096 points x 2 M rays = 8.4e9 rays through
 sample -> 12-surface trace -> DP weights -> bilinear splat -> normalise, i.e. 4096 (L, R) PSF pairs.  Consecutive
-steps walk the 32 depth slabs with stride 11 (near, in-focus and far depths alike).  With N GPUs every rank works on its own slab (weak scaling, no collective on
-the data path); `value` is the whole-job rays/s = N x slab rays / max-over-ranks device time.
+steps walk the 32 depth slabs with stride 11 (near, in-focus and far depths alike).  With N GPUs the job is an N times denser
+field sampling of the same bank: every rank works on its own (sub-cell shifted) 64x64 field grid of the step's slab (weak
+scaling, equal work per rank, no collective on the data path); `value` is the whole-job rays/s = N x slab rays /
+max-over-ranks device time.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--numerics strict|hybrid|fast] [--impl reference]
 
@@ -40,13 +42,20 @@ D_SENSOR = {"rf50mm": 62.25, "rf35mm": 80.447}
 # ----------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------
-def bank_points(slab):
+def bank_points(slab, rank=0, world=1):
     """Normalised (x, y, depth) of depth slab `slab` (0..31): cell-centred 64x64 field grid (psfnet.py:221-225 with
-    64 cells) at the slab's depth, z from the get_test_data warp of linspace(-3, 3, 32) (psfnet.py:229-232)."""
+    64 cells) at the slab's depth, z from the get_test_data warp of linspace(-3, 3, 32) (psfnet.py:229-232).
+    With `world` GPUs the job is a `world` times denser field sampling of the same bank: rank r takes the same grid moved to
+    the r-th of m x m sub-cell centres (m = ceil(sqrt(world))), so every rank traces different points of equal cost."""
     import torch
     g = GRID
-    x, y = torch.meshgrid(torch.linspace(-1 + 1 / (2 * g), 1 - 1 / (2 * g), g),
-                          torch.linspace(1 - 1 / (2 * g), -1 + 1 / (2 * g), g), indexing="xy")
+    m = 1
+    while m * m < world:
+        m += 1
+    cell = 1.0 / g                      # the grid's margin to the field edge is 1 / (2 g): shifted copies stay inside [-1, 1]
+    ox, oy = (((rank % m) + 0.5) / m - 0.5) * cell, (((rank // m) + 0.5) / m - 0.5) * cell
+    x, y = torch.meshgrid(torch.linspace(-1 + 1 / (2 * g), 1 - 1 / (2 * g), g) + ox,
+                          torch.linspace(1 - 1 / (2 * g), -1 + 1 / (2 * g), g) + oy, indexing="xy")
     d_min, d_max, ds = -200.0, -20000.0, D_SENSOR[LENS]
     foc_z = ((-1000.0 + ds) - d_min) / (d_max - d_min)
     zg = torch.linspace(-3, 3, DEPTHS)[slab % DEPTHS]
@@ -56,9 +65,11 @@ def bank_points(slab):
 
 
 def slab_of_step(step, rank=0, world=1):
-    """Depth slab (0..31) a given step of a given rank works on: a fixed stride-11 walk through the 32 depths, so that
-    any few consecutive steps sample near, in-focus and far slabs alike (cost per ray varies with depth)."""
-    return ((step * world + rank) * 11) % DEPTHS
+    """Depth slab (0..31) a given step works on: a fixed stride-11 walk through the 32 depths, so that any few consecutive
+    steps sample near, in-focus and far slabs alike (cost per ray varies with depth).  The same slab on every rank (each
+    rank has its own field points of it, see bank_points): the ranks' steps cost the same and weak scaling measures the
+    machine, not the luck of the depth draw."""
+    return (step * 11) % DEPTHS
 
 
 class ClockSampler(threading.Thread):
@@ -149,7 +160,8 @@ def run_reference(args):
 def workload_config(numerics):
     return {"workload": f"{LENS} F/4 PSF bank, {GRID}x{GRID} field x {DEPTHS} depths, {SPP} rays/point, ks={KS}, "
                         f"sensor {SENSOR_RES[0]}x{SENSOR_RES[1]}; step = one depth slab ({GRID * GRID} points), slabs visited "
-                        f"with stride 11 over the {DEPTHS} depths",
+                        f"with stride 11 over the {DEPTHS} depths; N GPUs = N sub-cell-shifted copies of the field grid at the "
+                        f"same slab (N times denser field sampling, equal work per rank)",
             "lens": LENS, "points_per_step": GRID * GRID, "rays_per_point": SPP, "ks": KS, "numerics": numerics,
             "l2": "L2 flushed (256 MiB write) between timed steps; the 16 MB shared pupil-sample set is re-read from L2 "
                   "by every point inside a step by design"}
@@ -202,7 +214,7 @@ def run_gpu(args):
         pupil = E.pupil_sort(pupil, pr)                            # one-off spatial ordering of the shared sample set
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     total_steps = args.warmup + args.steps
-    slabs = [lens._object_points(bank_points(slab_of_step(s, rank, world))).to(dev).contiguous() for s in range(total_steps)]
+    slabs = [lens._object_points(bank_points(slab_of_step(s, rank, world), rank, world)).to(dev).contiguous() for s in range(total_steps)]
     centres = [E.psf_centre(handle, 0.589, p, cpupil, pz, numerics=args.numerics) for p in slabs]
     n_pts = slabs[0].shape[0]
 
@@ -241,7 +253,7 @@ def run_gpu(args):
     pinned_out = [torch.empty((n_pts, 2, KS, KS), dtype=torch.float32).pin_memory() for _ in range(2)]
     done = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_steps = max(2, min(args.steps, 4))
-    host_pts = [bank_points(slab_of_step(s, rank, world)) for s in range(e2e_steps + 1)]
+    host_pts = [bank_points(slab_of_step(s, rank, world), rank, world) for s in range(e2e_steps + 1)]
     host_sum = [0.0]
 
     def enqueue(i):
