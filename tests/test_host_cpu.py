@@ -127,6 +127,13 @@ def test_bench_workload_shape():
     assert p.shape == (4096, 3) and abs(float(p[0, 0]) + 127 / 128) < 1e-6 and abs(float(p[0, 1]) - 127 / 128) < 1e-6
     depths = [float(bench.bank_points(s)[0, 2]) for s in range(32)]
     assert min(depths) >= -20000 - 1e-3 and max(depths) <= -200 + 1e-3 and len(set(depths)) == 32
+    # N GPUs: the same slab on every rank, N distinct sub-cell-shifted field grids inside [-1, 1]; N = 1 is the plain grid
+    assert torch.equal(bench.bank_points(5, 0, 1), bench.bank_points(5))
+    for world in (2, 4, 8):
+        assert len({bench.slab_of_step(4, r, world) for r in range(world)}) == 1 and bench.slab_of_step(4, 0, world) == bench.slab_of_step(4)
+        pts = torch.cat([bench.bank_points(5, r, world) for r in range(world)])
+        assert float(pts[:, :2].abs().max()) < 1.0 and len(torch.unique((pts[:, :2] * 1e5).round(), dim=0)) == world * 4096
+        assert len(set(pts[:, 2].tolist())) == 1
 
 
 def test_fused_kernel_sass_is_tcgen05_cta_pairs():
