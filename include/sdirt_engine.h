@@ -96,13 +96,14 @@ typedef struct sdirt_lens sdirt_lens;   /* opaque */
  *                         sensor-pixel assignment identical to the reference's for >= 99.95 % of rays;
  *   SDIRT_NUMERICS_ADAPTIVE HYBRID only where that lattice is coarse: the reference computes the first hit as
  *                         o + d*t in float32, so its lateral position sits on a lattice of ulp(|o_x|), ulp(|o_y|);
- *                         above 1024 mm that is >= 1.2e-4 mm and shows in a 2 M-ray PSF (L1 2e-5 at 4 m off axis,
- *                         5e-5 at 8 m, 1.1e-4 at 20 m with FAST).  Points (rays) beyond that bound take the STRICT
- *                         first surface, the others FAST; the choice is uniform per object point. */
+ *                         above 2048 mm that is >= 2.4e-4 mm and shows in a 2 M-ray PSF (measured PSF L1 of FAST against
+ *                         the reference: <= 2e-5 up to 2048 mm off axis, 5e-5 at 2800 mm, 1.1e-4 at 7000 mm).  Points
+ *                         (rays) beyond that bound take the STRICT first surface, the others FAST; the choice is uniform
+ *                         per object point. */
 enum { SDIRT_NEWTON_REPLAY = 0, SDIRT_NEWTON_PER_RAY = 1 };
 enum { SDIRT_NUMERICS_STRICT = 0, SDIRT_NUMERICS_FAST = 1, SDIRT_NUMERICS_HYBRID = 2, SDIRT_NUMERICS_ADAPTIVE = 3 };
 /* ADAPTIVE: object points (rays) whose lateral coordinate max(|x|, |y|) exceeds this many mm get the STRICT first surface */
-#define SDIRT_ADAPTIVE_LATTICE_MM 1024.0f
+#define SDIRT_ADAPTIVE_LATTICE_MM 2048.0f
 typedef struct sdirt_options {
     int32_t newton_mode;
     int32_t numerics;
