@@ -778,3 +778,36 @@ def test_packed_strict_first_surface_is_bit_identical():
                                            C.c_void_p(mm.data_ptr()), C.c_void_p(ex.data_ptr()), None) == 0
         torch.cuda.synchronize()
         assert mm.tolist() == [0] * 8, (pt, mm.tolist(), ex.tolist())
+
+
+@pytest.mark.parametrize("name", ["rf50mm", "rf35mm"])
+def test_two_ray_kernel_equals_one_ray_loop(name):
+    """The packed two-rays-per-thread loop against the one-ray loop of the same kernel (SDIRT_DEBUG_SCALAR_STRICT=2): hit counts
+    identical, PSFs equal up to the order of the shared-memory float atomics -- for every numerics mode of the throughput path,
+    with a sample count that leaves odd run lengths."""
+    import os
+    from sdirt_b200 import _engine as E
+    h = engine_lens(name)
+    pz, pr = {"rf50mm": (22.51324462890625, 6.019352912902832), "rf35mm": (14.338210105895996, 4.767455577850342)}[name]
+    g = torch.Generator().manual_seed(4)
+    npts, spp = 24, 100003
+    xy = torch.rand(npts, 2, generator=g) * 2 - 1
+    depth = -(torch.rand(npts, generator=g) * 19800 + 200) + D_SENSOR[name]
+    scale = -depth * 0.43 / 21.633307652783937
+    pts = torch.stack([xy[:, 0] * scale * 18, xy[:, 1] * scale * 12, depth], -1).float().to(DEV)
+    th = torch.rand(spp, generator=g) * 2 * np.pi
+    rr = torch.sqrt(torch.rand(spp, generator=g) * pr ** 2)
+    pup = E.pupil_sort(torch.stack([rr * torch.cos(th), rr * torch.sin(th)], -1).to(DEV), pr)
+    centre = E.psf_centre(h, 0.589, pts, (pup[:2048] * 0.25).contiguous(), pz)
+    for numerics in ("fast", "hybrid", "adaptive"):
+        res = []
+        for flag in (None, "2"):
+            try:
+                if flag:
+                    os.environ["SDIRT_DEBUG_SCALAR_STRICT"] = flag
+                res.append(E.psf_bank(h, 0.589, pts, pup, pz, centre, 21, 0.046875, numerics=numerics, want_counts=True))
+            finally:
+                os.environ.pop("SDIRT_DEBUG_SCALAR_STRICT", None)
+        (L2, R2, c2), (L1, R1, c1) = res
+        assert torch.equal(c2, c1), numerics
+        assert (L2 - L1).abs().max().item() < 1e-5 and (R2 - R1).abs().max().item() < 1e-5, numerics
