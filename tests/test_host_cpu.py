@@ -169,3 +169,35 @@ def test_fused_band_shape_fills_rounds():
         assert rounds / -(-rounds // 1) > 0.95 and nb * rows * w <= max(PSFNet.render_band_pixels_fused, rows * w)
     stub.render_band_rows, stub.render_band_pixels = 8, 1           # set by hand: kept
     assert PSFNet._fused_band_shape(stub, 4, 512, 768) == (8, 1)
+
+
+def test_fused_mlp_layout_host_side():
+    """sdirt_mlp_fused_layout is host arithmetic: packed sizes of the flagship MLP (last layer: 21 kernel rows padded to 24
+    accumulator columns = 504 -> 512), smaller windows, and the shapes it refuses."""
+    import ctypes as C
+    from sdirt_b200 import _engine as E
+    lib = E.lib()
+
+    def shape(n1, dims):
+        sh = E.MlpShape()
+        sh.n_layers, sh.n1 = len(dims), n1
+        k = n1
+        for l, n in enumerate(dims):
+            sh.K[l], sh.N[l] = k, n
+            k = n
+        return sh
+
+    w_off, b_off, bias = (C.c_int64 * 12)(), (C.c_int32 * 12)(), C.c_int64(0)
+    sh = shape(128, [512] * 9 + [441])
+    nbytes = lib.sdirt_mlp_fused_layout(C.byref(sh), w_off, b_off, C.byref(bias))
+    assert nbytes == 2 * (512 * 128 + 8 * 512 * 512 + 512 * 512) == 4849664          # last layer packed as 512 rows
+    assert bias.value == 10 * 512 and list(b_off[:10]) == [512 * i for i in range(10)]
+    assert w_off[1] == 2 * 512 * 128 and w_off[9] == 2 * (512 * 128 + 8 * 512 * 512)
+    sh = shape(64, [256, 128, 49])                                                     # ks = 7: 7 rows of 8 columns = 56 -> 64
+    assert lib.sdirt_mlp_fused_layout(C.byref(sh), None, None, C.byref(bias)) == 2 * (256 * 64 + 128 * 256 + 64 * 128)
+    assert bias.value == 256 + 128 + 64
+    sh = shape(128, [512, 121])                                                        # ks = 11: 11 rows of 12 columns = 132 -> 144
+    assert lib.sdirt_mlp_fused_layout(C.byref(sh), None, None, C.byref(bias)) == 2 * (512 * 128 + 144 * 512)
+    for bad in (shape(128, [512, 100]), shape(128, [100, 441]), shape(96, [512, 441]), shape(128, [640, 441])):
+        assert lib.sdirt_mlp_fused_layout(C.byref(bad), None, None, None) == -1
+        assert lib.sdirt_last_error()
