@@ -32,7 +32,7 @@ def main():
         if mode is None or (numerics if mode == "per_ray" else "replay") not in want:
             continue
         import functools
-        pup = pup_raw if numerics == 'strict' else pup_sorted
+        pup = pup_raw if (numerics == 'strict' and not os.environ.get('QB_STRICT_SORTED')) else pup_sorted
         E.psf_bank = functools.partial(E.psf_bank.func if hasattr(E.psf_bank, "func") else E.psf_bank, numerics=numerics)
         for _ in range(2):
             L, R, cnt = E.psf_bank(h, 0.589, pts, pup, pz, centre, 21, 0.046875, newton=mode, want_counts=True)
