@@ -201,3 +201,14 @@ def test_fused_mlp_layout_host_side():
     for bad in (shape(128, [512, 100]), shape(128, [100, 441]), shape(96, [512, 441]), shape(128, [640, 441])):
         assert lib.sdirt_mlp_fused_layout(C.byref(bad), None, None, None) == -1
         assert lib.sdirt_last_error()
+
+
+def test_every_exported_symbol_is_documented():
+    """The drop-in boundary is the header: every entry point it declares appears, by its full name, in INTEGRATION.md's table of
+    what it replaces in the reference."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "sdirt_engine.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(sdirt_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    assert [n for n in names if n not in doc] == []
