@@ -278,6 +278,12 @@ int sdirt_gamma_noise_clip(float *x_dev, const float *randn_dev, const float *no
 int sdirt_debug_strict_pair(const sdirt_lens *lens, double wvln_um, const float *point_dev, const float *pupil_xy_dev, int64_t n_samples,
                             double pupil_z, int *mismatch_dev, float *example_dev, void *stream);
 
+/* Testing aid: the m rays from one object point towards pupil_xy[m,2], traced by the packed (two rays per thread) strict tracer of
+ * the specialised parity kernel (csrc/strict_path.cuh) and propagated to the sensor: out_dev[m,7] = (o, d, alive).  Compared bit
+ * for bit with sdirt_trace_rays (numerics STRICT, per-ray Newton) by the tests. */
+int sdirt_debug_trace_strict2(const sdirt_lens *lens, double wvln_um, const float *point_dev, const float *pupil_xy_dev, int64_t n_samples,
+                              double pupil_z, float *out_dev, void *stream);
+
 int sdirt_fp32_peak_probe(float *out_dev, int blocks, int threads, int iters, void *stream);
 
 #ifdef __cplusplus

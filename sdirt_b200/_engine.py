@@ -5,7 +5,8 @@ import os
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libsdirt_engine.so")
+# SDIRT_ENGINE_LIB: another build of the same library (kernel-tuning A/B runs on the GPU box: tools/build_variants.py)
+_LIB_PATH = os.environ.get("SDIRT_ENGINE_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libsdirt_engine.so")
 MAX_SURFACES, MAX_AI, MAX_POINTS_PER_CALL = 32, 8, 65535
 SURF_FLAT, SURF_SPHERE, SURF_ASPHERE = 0, 1, 2
 
@@ -86,6 +87,7 @@ def lib():
     L.sdirt_tone_degamma.argtypes = [vp, vp, i64, vp]
     L.sdirt_gamma_noise_clip.argtypes = [vp, vp, vp, vp, cint, cint, cint, cint, vp]
     L.sdirt_fp32_peak_probe.argtypes = [vp, cint, cint, cint, vp]
+    L.sdirt_debug_trace_strict2.argtypes = [vp, dbl, vp, vp, i64, dbl, vp, vp]
     _lib = L
     return L
 
@@ -433,4 +435,14 @@ def gamma_noise_clip(x, randn, noise_range, weight):
 def fp32_peak_probe(device, blocks, threads, iters):
     out = torch.empty(blocks * threads, device=device, dtype=torch.float32)
     _check(lib().sdirt_fp32_peak_probe(_dev(out, "out"), blocks, threads, iters, _stream(out)))
+    return out
+
+
+def debug_trace_strict2(lens, wvln, point, pupil_xy, pupil_z):
+    """Testing aid: sensor-plane states [m, 7] = (o, d, alive) of the m rays from one object point, traced by the packed strict
+    tracer of the specialised parity kernel (csrc/strict_path.cuh)."""
+    m = pupil_xy.shape[0]
+    out = torch.zeros((m, 7), device=point.device, dtype=torch.float32)
+    _check(lib().sdirt_debug_trace_strict2(lens._h, float(wvln), _dev(point, "point"), _dev(pupil_xy, "pupil_xy"), m, float(pupil_z),
+                                           _dev(out, "out"), _stream(point)))
     return out

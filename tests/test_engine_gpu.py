@@ -142,12 +142,19 @@ def test_pixel_assignment_statistics():
                          (np.broadcast_to(obj[None], (spp, 6, 3)),)], 0)
     ray0 = O.rays_from_points(obj, px, py, pz)
     res = {}
+    pup = cu(np.stack([px, py], -1))
     for label, kw in (("replay", dict(newton=counts, numerics="strict")), ("per_ray", dict(newton="per_ray", numerics="strict")),
-                      ("hybrid", dict(numerics="hybrid")), ("fast", dict(numerics="fast"))):
-        o, d = cu(ray0.o().reshape(-1, 3)), cu(ray0.d().reshape(-1, 3))
-        ra = torch.ones(o.shape[0], device=DEV)
-        E.trace_rays(h, 0.589, o, d, ra, to_sensor=True, **kw)
-        got = np.concatenate([o.cpu().numpy(), d.cpu().numpy(), ra.cpu().numpy()[:, None]], -1).reshape(spp, 6, 7)
+                      ("strict_pair", None), ("hybrid", dict(numerics="hybrid")), ("adaptive", dict(numerics="adaptive")),
+                      ("fast", dict(numerics="fast"))):
+        if kw is None:
+            # the tracer of the specialised parity kernel (two rays per thread, csrc/strict_path.cuh): what `sdirt_psf_bank`
+            # runs for numerics = strict, and what bench.py reports as its tolerance-conformant line
+            got = np.stack([E.debug_trace_strict2(h, 0.589, cu(obj[p]), pup, pz).cpu().numpy() for p in range(6)], 1)
+        else:
+            o, d = cu(ray0.o().reshape(-1, 3)), cu(ray0.d().reshape(-1, 3))
+            ra = torch.ones(o.shape[0], device=DEV)
+            E.trace_rays(h, 0.589, o, d, ra, to_sensor=True, **kw)
+            got = np.concatenate([o.cpu().numpy(), d.cpu().numpy(), ra.cpu().numpy()[:, None]], -1).reshape(spp, 6, 7)
         mine = O.RayBundle(*(got[..., i].copy() for i in range(7)))
         have = pixels(mine)
         agree = (have[0] == want[0]) & (have[1] == want[1]) & (have[2] == want[2])
@@ -155,10 +162,12 @@ def test_pixel_assignment_statistics():
         print(label, "pixel agreement per point", agree.mean(0), "max |dx| mm", np.abs(mine.ox - ray.ox).max())
     assert res["replay"].min() == 1.0
     assert res["per_ray"].min() >= 0.9999
+    assert res["strict_pair"].min() >= 0.9999 and np.array_equal(res["strict_pair"], res["per_ray"])
     # hybrid / fast state the same geometry with different (more accurate, see test_fast_closer_to_float64)
     # roundings; only a bit-exact restatement can meet 99.99 % because the reference's own float32 noise on the
     # sensor plane (4e-6 .. 7e-5 mm mean) is larger than the 1.2e-6 mm the criterion leaves.  Measured floors:
     assert res["hybrid"].min() >= 0.9995
+    assert res["adaptive"].min() >= 0.997      # FAST below 2048 mm off axis, HYBRID beyond: between the two
     assert res["fast"].min() >= 0.997
 
 
@@ -262,6 +271,7 @@ def test_fast_closer_to_float64():
 
 def test_psf_bank_vs_oracle_small_and_ragged():
     """Seeded inputs at oracle-sized scale, incl. ragged sample counts and a point that is fully vignetted."""
+    import os
     from sdirt_b200 import _engine as E
     name = "rf50mm"
     lens = make_lens(name, 0.40959781408309937)
@@ -281,9 +291,20 @@ def test_psf_bank_vs_oracle_small_and_ragged():
                                newton_iters="per_ray")
         L, R, cnt = E.psf_bank(h, 0.589, cu(obj), cu(np.stack([px, py], -1)), 22.5132, cu(centre), 21, lens.pixel_size,
                                normalise=0, want_counts=True)
-        np.testing.assert_allclose(L.cpu().numpy(), Lo, rtol=1e-5, atol=2e-5)
-        np.testing.assert_allclose(R.cpu().numpy(), Ro, rtol=1e-5, atol=2e-5)
+        # the specialised parity kernel reads d_l / d_r from the table (<= 2e-5 of a weight next to the square-root
+        # singularities of the segment areas); the generic kernel evaluates the closed forms per ray
+        np.testing.assert_allclose(L.cpu().numpy(), Lo, rtol=5e-5, atol=2e-5)
+        np.testing.assert_allclose(R.cpu().numpy(), Ro, rtol=5e-5, atol=2e-5)
         assert cnt[6].item() == 0 and float(L[6].abs().sum()) == 0.0
+        os.environ["SDIRT_DEBUG_GENERIC_STRICT"] = "1"
+        try:
+            Lg, Rg, cg = E.psf_bank(h, 0.589, cu(obj), cu(np.stack([px, py], -1)), 22.5132, cu(centre), 21, lens.pixel_size,
+                                    normalise=0, want_counts=True)
+        finally:
+            os.environ.pop("SDIRT_DEBUG_GENERIC_STRICT", None)
+        np.testing.assert_allclose(Lg.cpu().numpy(), Lo, rtol=1e-5, atol=2e-5)
+        np.testing.assert_allclose(Rg.cpu().numpy(), Ro, rtol=1e-5, atol=2e-5)
+        assert torch.equal(cg, cnt)
     # empty point list is a no-op
     L, R = E.psf_bank(h, 0.589, cu(np.zeros((0, 3))), cu(np.zeros((4, 2))), 22.5, cu(np.zeros((0, 2))), 21, lens.pixel_size)
     assert L.shape == (0, 21, 21)
@@ -811,3 +832,66 @@ def test_two_ray_kernel_equals_one_ray_loop(name):
         (L2, R2, c2), (L1, R1, c1) = res
         assert torch.equal(c2, c1), numerics
         assert (L2 - L1).abs().max().item() < 1e-5 and (R2 - R1).abs().max().item() < 1e-5, numerics
+
+
+@pytest.mark.parametrize("name", ["rf50mm", "rf35mm"])
+def test_strict_pair_tracer_is_bit_identical(name):
+    """The specialised parity kernel's tracer (lens structure compiled in, two rays per thread in packed fp32, the exact
+    restatements listed in csrc/strict_path.cuh) against the generic one-ray strict trace with the per-ray Newton schedule:
+    validity flags equal and every field of every surviving ray bit-equal at the sensor plane -- near, far, on-axis and
+    field-corner object points, an odd sample count."""
+    from sdirt_b200 import _engine as E
+    h = engine_lens(name)
+    pz, pr = {"rf50mm": (22.51324462890625, 6.019352912902832), "rf35mm": (14.338210105895996, 4.767455577850342)}[name]
+    g = torch.Generator().manual_seed(7)
+    m = 100001
+    th = torch.rand(m, generator=g) * 2 * np.pi
+    rr = torch.sqrt(torch.rand(m, generator=g) * pr ** 2)
+    pup = torch.stack([rr * torch.cos(th), rr * torch.sin(th)], -1).to(DEV).contiguous()
+    ds = D_SENSOR[name]
+    pts = [[0.0, 0.0, -2000 + ds], [-86.98888, 2320.7637, -12153.938], [-5909.853, -2731.2825, -17124.674], [3.0, 2.0, -500.0 + ds],
+           [250.0, -160.0, -999.0 + ds], [7000.0, 4500.0, -20000.0 + ds], [60.0, 95.0, -200.0 + ds]]
+    alive_total = 0
+    for pt in pts:
+        p = torch.tensor(pt, device=DEV)
+        got = E.debug_trace_strict2(h, 0.589, p, pup, pz)
+        o, d = E.sample_rays(p.reshape(1, 3), pup, pz)
+        o, d = o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
+        ra = torch.ones(m, device=DEV)
+        E.trace_rays(h, 0.589, o, d, ra, to_sensor=True, newton="per_ray", numerics="strict")
+        want = torch.cat([o, d, ra[:, None]], -1)
+        assert torch.equal(got[:, 6], want[:, 6]), (pt, int((got[:, 6] != want[:, 6]).sum()))
+        keep = want[:, 6] > 0
+        alive_total += int(keep.sum())
+        same = (got[keep].view(torch.int32) == want[keep].view(torch.int32)).all(-1)
+        assert bool(same.all()), (pt, int((~same).sum()), (got[keep] - want[keep]).abs().max().item())
+    assert alive_total > 2 * m
+
+
+@pytest.mark.parametrize("name", ["rf50mm", "rf35mm"])
+def test_strict_bank_specialised_vs_generic(name):
+    """sdirt_psf_bank(numerics = strict) on the specialised kernel against the generic one-ray strict kernel
+    (SDIRT_DEBUG_GENERIC_STRICT=1): the same rays reach the window (hit counts identical) and the PSFs agree to the error of the
+    d_l / d_r table (<= 1e-5 of a weight) and the order of the float32 sums."""
+    import os
+    from sdirt_b200 import _engine as E
+    h = engine_lens(name)
+    lens, obj, pup, pz, pr, centre = _bank_inputs(name, n_pts=10, spp=60001, seed=12)
+    pts, pup, centre = cu(obj), cu(pup), cu(centre)
+    pup_sorted = E.pupil_sort(pup, float(pr))
+    res = []
+    for flag in (None, "1"):
+        try:
+            if flag:
+                os.environ["SDIRT_DEBUG_GENERIC_STRICT"] = flag
+            res.append(E.psf_bank(h, 0.589, pts, pup_sorted, pz, centre, 21, 0.046875, numerics="strict", normalise=0, want_counts=True))
+        finally:
+            os.environ.pop("SDIRT_DEBUG_GENERIC_STRICT", None)
+    (Ls, Rs, cs), (Lg, Rg, cg) = res
+    assert torch.equal(cs, cg)
+    assert l1_sumnorm(Ls.cpu().numpy(), Lg.cpu().numpy()).max() < 1e-5
+    assert l1_sumnorm(Rs.cpu().numpy(), Rg.cpu().numpy()).max() < 1e-5
+    # unsorted samples take the same kernel (shorter register runs, same sums)
+    Lu, Ru, cu_ = E.psf_bank(h, 0.589, pts, pup, pz, centre, 21, 0.046875, numerics="strict", normalise=0, want_counts=True)
+    assert torch.equal(cu_, cg)
+    assert l1_sumnorm(Lu.cpu().numpy(), Lg.cpu().numpy()).max() < 1e-5
