@@ -210,8 +210,7 @@ def run_gpu(args):
     rho = torch.sqrt(torch.rand(SPP) * pr ** 2)
     pupil = torch.stack((rho * torch.cos(theta), rho * torch.sin(theta)), 1).to(dev).contiguous()
     cpupil = (pupil[:2048] * 0.25).contiguous()
-    if args.numerics != "strict":
-        pupil = E.pupil_sort(pupil, pr)                            # one-off spatial ordering of the shared sample set
+    pupil = E.pupil_sort(pupil, pr)                                # one-off spatial ordering of the shared sample set
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     total_steps = args.warmup + args.steps
     slabs = [lens._object_points(bank_points(slab_of_step(s, rank, world), rank, world)).to(dev).contiguous() for s in range(total_steps)]
@@ -342,7 +341,7 @@ def run_gpu(args):
     torch.manual_seed(1234)
     raw = torch.stack((rho * torch.cos(theta), rho * torch.sin(theta)), 1).to(dev).contiguous()
     for mode in ("strict", "hybrid", "adaptive", "fast"):
-        pup = raw if mode == "strict" else pupil
+        pup = pupil
         ms = timed(lambda: E.psf_bank(handle, 0.589, sub, pup, pz, subc, KS, lens.pixel_size, numerics=mode), 2)
         modes[mode] = sub.shape[0] * SPP / (ms * 1e-3)
     rb, rh, rw = 2, 1024, 1536

@@ -84,10 +84,23 @@ __device__ __forceinline__ void sag_slope_strict2(const SurfDev &s, f2 r2, f2 &g
     f2 kr2c2, hkr2c2;
     if (KIND == SIG_SPHERE) { kr2c2 = mul2s(r2, bc2(s.c2)); hkr2c2 = mul2s(r2, bc2(0.5f * s.c2)); }
     else { const f2 kr2 = mul2s(bc2(s.onek), r2); kr2c2 = mul2s(kr2, bc2(s.c2)); hkr2c2 = mul2s(kr2, bc2(0.5f * s.c2)); }
+#if SDIRT_STRICT_SHORT_DIV
+    // sqrt_rn2 keeping its MUFU.RSQ seed y ~ 1 / sf (2^-22): the reciprocal of the quotient (r2 c2 / 2) / sf.  That quotient is a
+    // small correction added to 1 + sf, so even the rare last-bit difference from the IEEE quotient (2e-6 of them by the bound
+    // above) survives the sum's rounding one time in ~30.
+    const f2 x = add2(bc2(1.0f), neg2(kr2c2));
+    const f2 y = rsq2(x);
+    const f2 sq = mul2(x, y);
+    const f2 sf = fma2(fma2(neg2(sq), sq, x), mul2(y, bc2(0.5f)), sq);
+    const f2 q0 = mul2(hkr2c2, y);
+    const f2 inner = fma2(y, fma2(neg2(sf), q0, hkr2c2), q0);
+#else
     const f2 sf = sqrt_rn2(add2(bc2(1.0f), neg2(kr2c2)));
+    const f2 inner = sdiv2(hkr2c2, sf);
+#endif
     const f2 one_sf = add2(bc2(1.0f), sf);
     if (WANT_G) g = sdiv2(mul2s(r2, bc2(s.c)), one_sf);
-    dg = sdiv2(mul2s(add2(one_sf, sdiv2(hkr2c2, sf)), bc2(s.c)), mul2s(one_sf, one_sf));
+    dg = sdiv2(mul2s(add2(one_sf, inner), bc2(s.c)), mul2s(one_sf, one_sf));
     if constexpr (KIND == SIG_ASPHERE && NAI > 0) poly_terms2<NAI, WANT_G>(s, r2, g, dg);
 }
 
@@ -261,10 +274,11 @@ static bool strict_loop_ok(const LensDev &L) {
 }
 
 #ifndef SDIRT_STRICT_MIN_CTAS
-#define SDIRT_STRICT_MIN_CTAS 3       // 256-thread CTAs per SM: 80 registers per thread for the pair's state + the Newton loop
+#define SDIRT_STRICT_MIN_CTAS 4       // 256-thread CTAs per SM: 64 registers per thread (measured 2 % faster than 3 x 80 despite ~200 B of spills)
 #endif
 struct TraceStrictLoop {
     static constexpr bool PAIR = true;
+    static constexpr bool ONE_RAY_LOOP = false;      // no one-ray variant of the loop in this kernel (the generic kernel is the comparison)
     static constexpr bool STRICT_SPLAT = true;
     static constexpr int MIN_CTAS = SDIRT_STRICT_MIN_CTAS;
     static __device__ __forceinline__ bool trace(const LensDev &L, RayReg &r, bool) {      // one-ray loop (debug switch): the generic strict trace

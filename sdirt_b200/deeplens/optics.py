@@ -263,7 +263,10 @@ class Lensgroup(DeepObj):
             points = points.unsqueeze(0)
         point_obj = self._object_points(points)
         pts = point_obj.to(self.device).contiguous()
-        xy, pupilz = self._pupil_samples(spp, spatial_order=self.numerics in ("fast", "hybrid", "adaptive"))   # main bundle first ...
+        # (the run-length splat of the specialised kernels wants neighbouring samples in a row; the generic strict kernel that
+        # replays given Newton loop counts splats with shared-memory atomics and is faster on the unsorted set)
+        xy, pupilz = self._pupil_samples(spp, spatial_order=self.numerics in ("fast", "hybrid", "adaptive")
+                                         or self.newton == "per_ray")                                   # main bundle first ...
         if center:
             centre = self.psf_center(point_obj)                          # ... then the chief-ray bundle (RNG order)
         else:
