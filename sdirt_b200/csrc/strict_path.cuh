@@ -55,6 +55,9 @@ __device__ __forceinline__ void poly_terms2(const SurfDev &s, f2 r2, f2 &g, f2 &
 #ifndef SDIRT_STRICT_SHORT_DIV
 #define SDIRT_STRICT_SHORT_DIV 1
 #endif
+#ifndef SDIRT_STRICT_RCP_SQUARE
+#define SDIRT_STRICT_RCP_SQUARE 0     // experiment: relieve the XU pipe (one MUFU.RCP less per evaluation) at one more packed multiply
+#endif
 __device__ __forceinline__ f2 sdiv2(f2 a, f2 b) {
 #if SDIRT_STRICT_SHORT_DIV
     const f2 r = rcp2(b);
@@ -81,26 +84,35 @@ __device__ __forceinline__ void sdiv2x3(f2 a0, f2 a1, f2 a2, f2 b, f2 &q0, f2 &q
 // (r2 c2) / 2 is taken as r2 (c2 / 2): scaling by a power of two commutes with rounding.
 template <int KIND, int NAI, bool WANT_G>
 __device__ __forceinline__ void sag_slope_strict2(const SurfDev &s, f2 r2, f2 &g, f2 &dg) {
-    f2 kr2c2, hkr2c2;
-    if (KIND == SIG_SPHERE) { kr2c2 = mul2s(r2, bc2(s.c2)); hkr2c2 = mul2s(r2, bc2(0.5f * s.c2)); }
-    else { const f2 kr2 = mul2s(bc2(s.onek), r2); kr2c2 = mul2s(kr2, bc2(s.c2)); hkr2c2 = mul2s(kr2, bc2(0.5f * s.c2)); }
+    const f2 kr2c2 = KIND == SIG_SPHERE ? mul2s(r2, bc2(s.c2)) : mul2s(mul2s(bc2(s.onek), r2), bc2(s.c2));
 #if SDIRT_STRICT_SHORT_DIV
-    // sqrt_rn2 keeping its MUFU.RSQ seed y ~ 1 / sf (2^-22): the reciprocal of the quotient (r2 c2 / 2) / sf.  That quotient is a
-    // small correction added to 1 + sf, so even the rare last-bit difference from the IEEE quotient (2e-6 of them by the bound
-    // above) survives the sum's rounding one time in ~30.
+    // sqrt_rn2 keeping its MUFU.RSQ seed y ~ 1 / sf (2^-22) as the reciprocal of the quotient by sf.  The reference's term is
+    // ((r2 c2) / 2) / sf; TWICE that, (r2 c2) / sf, is the same quotient up to the exact scaling, and the halving rides in the
+    // sum that uses it: (1 + sf) + q / 2 == fma(0.5, q, 1 + sf).  The term is a small correction to 1 + sf, so even the rare
+    // last-bit difference from the IEEE quotient (2e-6 of them by the bound above) survives that sum's rounding one time in ~30.
     const f2 x = add2(bc2(1.0f), neg2(kr2c2));
     const f2 y = rsq2(x);
     const f2 sq = mul2(x, y);
     const f2 sf = fma2(fma2(neg2(sq), sq, x), mul2(y, bc2(0.5f)), sq);
-    const f2 q0 = mul2(hkr2c2, y);
-    const f2 inner = fma2(y, fma2(neg2(sf), q0, hkr2c2), q0);
+    const f2 q0 = mul2(kr2c2, y);
+    const f2 inner2 = fma2(y, fma2(neg2(sf), q0, kr2c2), q0);
+    const f2 one_sf = add2(bc2(1.0f), sf);
+    const f2 s1 = fma2(bc2(0.5f), inner2, one_sf);
 #else
     const f2 sf = sqrt_rn2(add2(bc2(1.0f), neg2(kr2c2)));
-    const f2 inner = sdiv2(hkr2c2, sf);
-#endif
     const f2 one_sf = add2(bc2(1.0f), sf);
+    const f2 s1 = add2(one_sf, sdiv2(mul2s(kr2c2, bc2(0.5f)), sf));
+#endif
+#if SDIRT_STRICT_SHORT_DIV && SDIRT_STRICT_RCP_SQUARE
+    // one MUFU.RCP for both divisors: 1 / (1+sf) for g, its square as the reciprocal of fl((1+sf)^2) for the slope
+    const f2 r1 = rcp2(one_sf);
+    if (WANT_G) { const f2 num = mul2s(r2, bc2(s.c)); const f2 q = mul2(num, r1); g = fma2(r1, fma2(neg2(one_sf), q, num), q); }
+    { const f2 num = mul2s(s1, bc2(s.c)), den = mul2s(one_sf, one_sf), rd = mul2(r1, r1);
+      const f2 q = mul2(num, rd); dg = fma2(rd, fma2(neg2(den), q, num), q); }
+#else
     if (WANT_G) g = sdiv2(mul2s(r2, bc2(s.c)), one_sf);
-    dg = sdiv2(mul2s(add2(one_sf, inner), bc2(s.c)), mul2s(one_sf, one_sf));
+    dg = sdiv2(mul2s(s1, bc2(s.c)), mul2s(one_sf, one_sf));
+#endif
     if constexpr (KIND == SIG_ASPHERE && NAI > 0) poly_terms2<NAI, WANT_G>(s, r2, g, dg);
 }
 
@@ -122,10 +134,11 @@ __device__ __forceinline__ void newton_eval2(const SurfDev &s, const Ray2 &r, f2
     f2 g, dg;
     sag_slope_strict2<KIND, NAI, true>(s, r2, g, dg);
     ftn = add2(add2(g, bc2(s.d)), neg2(nz));
-    const f2 dfdt = fma2(bc2(2.0f), mul2s(dg, add2(mul2s(a, t), b)), neg2(r.dz));
-    f2 step = sdiv2(ftn, add2(dfdt, bc2(EPS_F)));
-    step = make_float2(fminf(fmaxf(step.x, -NEWTON_STEP), NEWTON_STEP), fminf(fmaxf(step.y, -NEWTON_STEP), NEWTON_STEP));
-    tn = add2(t, neg2(step));
+    // -(f' + eps) instead of f' + eps (rounding is symmetric under negation): no negated copy of d_z is needed as an FMA addend
+    const f2 ndf = add2(fma2(bc2(-2.0f), mul2s(dg, add2(mul2s(a, t), b)), r.dz), bc2(-EPS_F));
+    f2 nstep = sdiv2(ftn, ndf);
+    nstep = make_float2(fminf(fmaxf(nstep.x, -NEWTON_STEP), NEWTON_STEP), fminf(fmaxf(nstep.y, -NEWTON_STEP), NEWTON_STEP));
+    tn = add2(t, nstep);
 }
 
 // Newton intersection (surfaces.py:523-586) for a pair of rays with the per-ray schedule: a half leaves the loose loop when ITS
@@ -140,7 +153,8 @@ __device__ __forceinline__ void newton_strict2(const SurfDev &s, const Ray2 &r, 
     const f2 a = add2(mul2s(r.dx, r.dx), mul2s(r.dy, r.dy));
     const f2 b = add2(mul2s(r.dx, r.ox), mul2s(r.dy, r.oy));
     f2 t = t0, tb = t0;
-    bool run0 = r.a0, run1 = r.a1;                     // still inside the loose loop (the first evaluation always runs: ft = 1e5)
+    bool run0 = true, run1 = true;                     // still inside the loose loop (the first evaluation always runs: ft = 1e5;
+                                                       // a dead half is NaN and leaves after it: |NaN| > tol is false)
     int it = 0;
 #pragma unroll 1
     do {
@@ -185,6 +199,15 @@ __device__ __forceinline__ void refract_strict2(const SurfDev &s, Ray2 &r, f2 qx
     r.dz = add2(mul2s(sr, qz), mul2s(bc2(s.eta), add2(r.dz, neg2(mul2s(cq, qz)))));
 }
 
+// Validity lives IN the ray in this tracer: a half that fails a surface's test gets d_z = NaN.  Every later quantity of that half is
+// then NaN (t0 = (d - o_z) / d_z first of all), every later validity test is a comparison and fails on NaN, and the crop test of the
+// splat drops it -- no alive flags to carry through the surface loop, no conjunctions with them (a ray whose arithmetic produces
+// NaN by itself is invalid in the reference for the same reason: its comparisons fail).
+__device__ __forceinline__ void strict_kill2(Ray2 &r, bool v0, bool v1) {
+    const float nan = __int_as_float(0x7fc00000);
+    r.dz = make_float2(v0 ? r.dz.x : nan, v1 ? r.dz.y : nan);
+}
+
 // Aspheric.ray_reaction (surfaces.py:391-520) for one surface of kind K (SIG_STOP covers every flat surface: whether it refracts
 // is a run-time flag) and a pair of rays; r.oz is ABSOLUTE here (the reference's coordinates), unlike the fast tracer's
 // vertex-relative z.  A dead half carries garbage that nothing reads.
@@ -195,16 +218,15 @@ __device__ __forceinline__ void strict_step2(const SurfDev &s, Ray2 &r) {
         r.ox = add2(r.ox, mul2s(t, r.dx)); r.oy = add2(r.oy, mul2s(t, r.dy)); r.oz = add2(r.oz, mul2s(t, r.dz));
         bool v0, v1;
         if (s.flags & F_SQUARE) {                                                            // surfaces.py:416-419
-            v0 = r.a0 && fabsf(r.ox.x) <= s.r && fabsf(r.oy.x) <= s.r;
-            v1 = r.a1 && fabsf(r.ox.y) <= s.r && fabsf(r.oy.y) <= s.r;
+            v0 = fabsf(r.ox.x) <= s.r && fabsf(r.oy.x) <= s.r;
+            v1 = fabsf(r.ox.y) <= s.r && fabsf(r.oy.y) <= s.r;
         } else {
             const f2 r2u = add2(mul2s(r.ox, r.ox), mul2s(r.oy, r.oy));
-            v0 = r.a0 && (r2u.x <= s.r2_sqrt_le);                                            // sqrt(x^2 + y^2) <= r, surfaces.py:421
-            v1 = r.a1 && (r2u.y <= s.r2_sqrt_le);
+            v0 = r2u.x <= s.r2_sqrt_le;                                                      // sqrt(x^2 + y^2) <= r, surfaces.py:421
+            v1 = r2u.y <= s.r2_sqrt_le;
         }
         if (s.flags & F_REFRACTS) refract_strict2(s, r, bc2(0.0f), bc2(0.0f), bc2(1.0f), 1.0f, v0, v1);   // n = -normalize((0,0,-1))
-        r.a0 = v0;
-        r.a1 = v1;
+        strict_kill2(r, v0, v1);
         return;
     }
     f2 t, ft_last;
@@ -214,16 +236,16 @@ __device__ __forceinline__ void strict_step2(const SurfDev &s, Ray2 &r) {
     bool v0, v1;
     f2 qx, qy, qz;
     if (K == SIG_SPHERE) {
-        v0 = r.a0 && (r2u.x <= s.r2) && (t.x >= 0.0f);                                       // surfaces.py:464
-        v1 = r.a1 && (r2u.y <= s.r2) && (t.y >= 0.0f);
+        v0 = (r2u.x <= s.r2) && (t.x >= 0.0f);                                               // surfaces.py:464
+        v1 = (r2u.y <= s.r2) && (t.y >= 0.0f);
         // gradient (+-2x, +-2y, +-(2z - 2(d+R))) = +-2 (x, y, w): the normalised vector is +-(x, y, w) / |(x, y, w)| bit for bit
         const f2 w = add2(r.oz, bc2(-s.dR));
         const f2 nrm = sqrt_rn2(fma2(w, w, fma2(r.oy, r.oy, mul2s(r.ox, r.ox))));             // norm3
         sdiv2x3(r.ox, r.oy, w, nrm, qx, qy, qz);
-        refract_strict2(s, r, qx, qy, qz, (s.flags & F_CPOS) ? -1.0f : 1.0f, v0, v1);
+        refract_strict2(s, r, qx, qy, qz, s.sigma, v0, v1);
     } else {
-        v0 = r.a0 && strict_mask(s, r2u.x) && (fabsf(ft_last.x) < NEWTON_TIGHT) && (t.x > 0.0f);   // surfaces.py:584
-        v1 = r.a1 && strict_mask(s, r2u.y) && (fabsf(ft_last.y) < NEWTON_TIGHT) && (t.y > 0.0f);
+        v0 = strict_mask(s, r2u.x) && (fabsf(ft_last.x) < NEWTON_TIGHT) && (t.x > 0.0f);           // surfaces.py:584
+        v1 = strict_mask(s, r2u.y) && (fabsf(ft_last.y) < NEWTON_TIGHT) && (t.y > 0.0f);
         f2 g, dg;
         sag_slope_strict2<K, NAI, false>(s, r2u, g, dg);                                      // (x, y masked by ra > 0: alive here)
         const f2 dg2 = mul2s(dg, bc2(2.0f));
@@ -232,8 +254,7 @@ __device__ __forceinline__ void strict_step2(const SurfDev &s, Ray2 &r) {
         sdiv2x3(gx, gy, bc2(-1.0f), nrm, qx, qy, qz);
         refract_strict2(s, r, qx, qy, qz, -1.0f, v0, v1);
     }
-    r.a0 = v0;
-    r.a1 = v1;
+    strict_kill2(r, v0, v1);
 }
 
 // One surface of any kind.  Polynomial orders compiled: 0 (pure conic), 4, 5, 6 coefficients; the cycle detection of the first
@@ -257,9 +278,11 @@ __device__ __forceinline__ void trace_strict_loop2(const LensDev &L, Ray2 &r) {
     strict_surface2<true>(L.s[0], r);
 #pragma unroll 1
     for (int j = 1; j < L.n; ++j) {
-        if (!(r.a0 || r.a1)) continue;                       // (no early exit: the loop counter stays warp-uniform)
+        if (r.dz.x != r.dz.x && r.dz.y != r.dz.y) continue;  // both halves dead (no early exit: the loop counter stays warp-uniform)
         strict_surface2<false>(L.s[j], r);
     }
+    r.a0 = r.dz.x == r.dz.x;
+    r.a1 = r.dz.y == r.dz.y;
 }
 
 // can the packed strict tracer take this (resolved) lens?  forward, per-ray Newton schedule, compiled polynomial orders
@@ -273,6 +296,9 @@ static bool strict_loop_ok(const LensDev &L) {
     return true;
 }
 
+#ifndef SDIRT_STRICT_BLOCK
+#define SDIRT_STRICT_BLOCK 16
+#endif
 #ifndef SDIRT_STRICT_MIN_CTAS
 #define SDIRT_STRICT_MIN_CTAS 4       // 256-thread CTAs per SM: 64 registers per thread (measured 2 % faster than 3 x 80 despite ~200 B of spills)
 #endif
@@ -281,6 +307,7 @@ struct TraceStrictLoop {
     static constexpr bool ONE_RAY_LOOP = false;      // no one-ray variant of the loop in this kernel (the generic kernel is the comparison)
     static constexpr bool STRICT_SPLAT = true;
     static constexpr int MIN_CTAS = SDIRT_STRICT_MIN_CTAS;
+    static constexpr int BLOCK = SDIRT_STRICT_BLOCK;     // samples per lane and block of the interleaved assignment (fast_path.cuh)
     static __device__ __forceinline__ bool trace(const LensDev &L, RayReg &r, bool) {      // one-ray loop (debug switch): the generic strict trace
         trace_lens<STRICT, false>(L, r, nullptr, 0, 0, false);
         return r.alive;
@@ -304,9 +331,14 @@ debug_trace_strict2_kernel(const __grid_constant__ LensDev L, const float *__res
     // Ray.propagate_to(d_sensor), basics.py:262-263
     const f2 t = div_rn2(add2(bc2(L.d_sensor), neg2(r.oz)), r.dz);
     const f2 sx = add2(r.ox, mul2s(r.dx, t)), sy = add2(r.oy, mul2s(r.dy, t)), sz = add2(r.oz, mul2s(r.dz, t));
-    float *p = out + j * 7;
-    p[0] = sx.x; p[1] = sy.x; p[2] = sz.x; p[3] = r.dx.x; p[4] = r.dy.x; p[5] = r.dz.x; p[6] = r.a0 ? 1.f : 0.f;
-    if (two) { p += 7; p[0] = sx.y; p[1] = sy.y; p[2] = sz.y; p[3] = r.dx.y; p[4] = r.dy.y; p[5] = r.dz.y; p[6] = r.a1 ? 1.f : 0.f; }
+    float *p = out + j * 7;                                 // (a dead ray's state is NaN inside the tracer: report zeros)
+    if (r.a0) { p[0] = sx.x; p[1] = sy.x; p[2] = sz.x; p[3] = r.dx.x; p[4] = r.dy.x; p[5] = r.dz.x; p[6] = 1.f; }
+    else { for (int k = 0; k < 7; ++k) p[k] = 0.f; }
+    if (two) {
+        p += 7;
+        if (r.a1) { p[0] = sx.y; p[1] = sy.y; p[2] = sz.y; p[3] = r.dx.y; p[4] = r.dy.y; p[5] = r.dz.y; p[6] = 1.f; }
+        else { for (int k = 0; k < 7; ++k) p[k] = 0.f; }
+    }
 }
 
 // The parity mode of sdirt_psf_bank (numerics STRICT, per-ray Newton schedule) on the packed kernel; returns 1 if the lens is
