@@ -244,6 +244,13 @@ def run_gpu(args):
     rays_per_step = n_pts * SPP
     value = world * rays_per_step * args.steps / (total_ms * 1e-3)
     assert torch.isfinite(out[0]).all() and float(out[0].max()) > 0.99
+    if args.quick:
+        if rank == 0:
+            os.write(real_stdout, (json.dumps({"quick": True, "numerics": args.numerics, "value": value, "ms_per_step": total_ms / args.steps,
+                                               "step_ms": step_ms, "lib": E._LIB_PATH}) + "\n").encode())
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the public API, host buffers in, host buffers out -------------------------
     # Double-buffered like any producer/consumer loop: while the GPU works on step i the host draws the sample set of step
@@ -416,6 +423,7 @@ def main():
     ap.add_argument("--impl", default="sdirt_b200", choices=["sdirt_b200", "reference"])
     ap.add_argument("--numerics", default="adaptive", choices=["strict", "hybrid", "adaptive", "fast"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="kernel-only number and exit (tuning runs; not a contract line)")
     ap.add_argument("--lens", default="rf50mm", choices=sorted(HFOV), help="prescription (rf50mm = the headline config)")
     args = ap.parse_args()
     global LENS, FLOP_PER_RAY

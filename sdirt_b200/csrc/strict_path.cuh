@@ -36,11 +36,14 @@ __device__ __forceinline__ void poly_terms2(const SurfDev &s, f2 r2, f2 &g, f2 &
 #pragma unroll
         for (int i = 4; i <= N; ++i) { q0 = q0 * x0; q1 = q1 * x1; p[i] = make_float2((float)q0, (float)q1); }
     }
+    // a2 = 0 (the usual case: the vertex curvature is carried by c): g + 0 * rho^2 and dg + 0 are g and dg themselves
+    const bool a2 = !(s.flags & F_A2ZERO);
     if (WANT_G) {
+        if (a2) g = add2(g, mul2s(bc2(s.ai[0]), p[1]));
 #pragma unroll
-        for (int i = 1; i <= N; ++i) g = add2(g, mul2s(bc2(s.ai[i - 1]), p[i]));
+        for (int i = 2; i <= N; ++i) g = add2(g, mul2s(bc2(s.ai[i - 1]), p[i]));
     }
-    dg = add2(dg, bc2(s.ai[0]));
+    if (a2) dg = add2(dg, bc2(s.ai[0]));
 #pragma unroll
     for (int i = 2; i <= N; ++i) dg = add2(dg, mul2s(bc2(s.dai[i - 1]), p[i - 1]));     // dai[i-1] = fl(i * ai[i-1])
 }
@@ -84,7 +87,8 @@ __device__ __forceinline__ void sdiv2x3(f2 a0, f2 a1, f2 a2, f2 b, f2 &q0, f2 &q
 // (r2 c2) / 2 is taken as r2 (c2 / 2): scaling by a power of two commutes with rounding.
 template <int KIND, int NAI, bool WANT_G>
 __device__ __forceinline__ void sag_slope_strict2(const SurfDev &s, f2 r2, f2 &g, f2 &dg) {
-    const f2 kr2c2 = KIND == SIG_SPHERE ? mul2s(r2, bc2(s.c2)) : mul2s(mul2s(bc2(s.onek), r2), bc2(s.c2));
+    // ((1 + k) r2) c2; with k = 0 (spheres, and aspheres whose conic constant is zero) the first product is r2 itself
+    const f2 kr2c2 = (KIND == SIG_SPHERE || (s.flags & F_KZERO)) ? mul2s(r2, bc2(s.c2)) : mul2s(mul2s(bc2(s.onek), r2), bc2(s.c2));
 #if SDIRT_STRICT_SHORT_DIV
     // sqrt_rn2 keeping its MUFU.RSQ seed y ~ 1 / sf (2^-22) as the reciprocal of the quotient by sf.  The reference's term is
     // ((r2 c2) / 2) / sf; TWICE that, (r2 c2) / sf, is the same quotient up to the exact scaling, and the halving rides in the
@@ -122,14 +126,9 @@ template <int KIND, int NAI, bool STRICT>
 __device__ __forceinline__ void newton_eval2(const SurfDev &s, const Ray2 &r, f2 a, f2 b, f2 t, f2 &ftn, f2 &tn) {
     const f2 nx = add2(r.ox, mul2s(r.dx, t)), ny = add2(r.oy, mul2s(r.dy, t)), nz = add2(r.oz, mul2s(r.dz, t));
     const f2 r2u = add2(mul2s(nx, nx), mul2s(ny, ny));
-    bool m0, m1;
-    if (KIND == SIG_SPHERE) {                               // k = 0 > -1: both masks are upper bounds on rho^2
-        const float thr = STRICT ? s.thr_strict : s.bound;
-        m0 = r2u.x < thr; m1 = r2u.y < thr;
-    } else {
-        m0 = STRICT ? strict_mask(s, r2u.x) : loose_mask(s, r2u.x);
-        m1 = STRICT ? strict_mask(s, r2u.y) : loose_mask(s, r2u.y);
-    }
+    // k > -1 (every surface this tracer accepts, strict_loop_ok): both masks are upper bounds on rho^2
+    const float thr = STRICT ? s.thr_strict : s.bound;
+    const bool m0 = r2u.x < thr, m1 = r2u.y < thr;
     const f2 r2 = make_float2(m0 ? r2u.x : 0.0f, m1 ? r2u.y : 0.0f);
     f2 g, dg;
     sag_slope_strict2<KIND, NAI, true>(s, r2, g, dg);
@@ -161,20 +160,22 @@ __device__ __forceinline__ void newton_strict2(const SurfDev &s, const Ray2 &r, 
         f2 ftn, tn;
         newton_eval2<KIND, NAI, false>(s, r, a, b, t, ftn, tn);
         ++it;
-        if (FIRST) {
+        if (FIRST && it >= 3) {
             // period 1 (t_new == t): every further evaluation repeats this one.  period 2 (t_new == the t before this
             // evaluation's input) with the residual still above the tolerance: t alternates until the cap, the parity of
-            // the evaluations left picks the survivor.
+            // the evaluations left picks the survivor.  Looked for from the third evaluation on (a ray that converges the
+            // ordinary way has left by then; a cycle that began earlier is still a cycle: same outcome, one evaluation later).
             const bool big0 = fabsf(ftn.x) > NEWTON_LOOSE, big1 = fabsf(ftn.y) > NEWTON_LOOSE;
             const bool p1x = tn.x == t.x, p1y = tn.y == t.y;
-            const bool p2x = !p1x && it >= 2 && tn.x == tb.x && big0;
-            const bool p2y = !p1y && it >= 2 && tn.y == tb.y && big1;
+            const bool p2x = !p1x && tn.x == tb.x && big0;
+            const bool p2y = !p1y && tn.y == tb.y && big1;
             const bool odd = ((NEWTON_MAXIT - it) & 1) != 0;
             if (run0) { tb.x = t.x; if (!(p2x && odd)) t.x = tn.x; }
             if (run1) { tb.y = t.y; if (!(p2y && odd)) t.y = tn.y; }
             run0 = run0 && big0 && !(p1x || p2x);
             run1 = run1 && big1 && !(p1y || p2y);
         } else {
+            if (FIRST) { if (run0) tb.x = t.x; if (run1) tb.y = t.y; }
             if (run0) t.x = tn.x;
             if (run1) t.y = tn.y;
             run0 = run0 && fabsf(ftn.x) > NEWTON_LOOSE;
@@ -191,8 +192,8 @@ __device__ __forceinline__ void refract_strict2(const SurfDev &s, Ray2 &r, f2 qx
     const f2 cq = add2(add2(mul2s(r.dx, qx), mul2s(r.dy, qy)), mul2s(r.dz, qz));
     const f2 c2 = mul2s(cq, cq);
     const f2 e = mul2s(bc2(s.eta2), add2(bc2(1.0f), neg2(c2)));
-    v0 = v0 && (c2.x > 0.1f) && (e.x < 1.0f);
-    v1 = v1 && (c2.y > 0.1f) && (e.y < 1.0f);
+    v0 = v0 & (c2.x > 0.1f) & (e.x < 1.0f);          // (plain conjunctions: one select on the combined predicate, not one per test)
+    v1 = v1 & (c2.y > 0.1f) & (e.y < 1.0f);
     const f2 sr = mul2(bc2(sigma), sqrt_rn2(add2(bc2(1.0f), neg2(e))));
     r.dx = add2(mul2s(sr, qx), mul2s(bc2(s.eta), add2(r.dx, neg2(mul2s(cq, qx)))));
     r.dy = add2(mul2s(sr, qy), mul2s(bc2(s.eta), add2(r.dy, neg2(mul2s(cq, qy)))));
@@ -236,16 +237,16 @@ __device__ __forceinline__ void strict_step2(const SurfDev &s, Ray2 &r) {
     bool v0, v1;
     f2 qx, qy, qz;
     if (K == SIG_SPHERE) {
-        v0 = (r2u.x <= s.r2) && (t.x >= 0.0f);                                               // surfaces.py:464
-        v1 = (r2u.y <= s.r2) && (t.y >= 0.0f);
+        v0 = (r2u.x <= s.r2) & (t.x >= 0.0f);                                                // surfaces.py:464
+        v1 = (r2u.y <= s.r2) & (t.y >= 0.0f);
         // gradient (+-2x, +-2y, +-(2z - 2(d+R))) = +-2 (x, y, w): the normalised vector is +-(x, y, w) / |(x, y, w)| bit for bit
         const f2 w = add2(r.oz, bc2(-s.dR));
         const f2 nrm = sqrt_rn2(fma2(w, w, fma2(r.oy, r.oy, mul2s(r.ox, r.ox))));             // norm3
         sdiv2x3(r.ox, r.oy, w, nrm, qx, qy, qz);
         refract_strict2(s, r, qx, qy, qz, s.sigma, v0, v1);
     } else {
-        v0 = strict_mask(s, r2u.x) && (fabsf(ft_last.x) < NEWTON_TIGHT) && (t.x > 0.0f);           // surfaces.py:584
-        v1 = strict_mask(s, r2u.y) && (fabsf(ft_last.y) < NEWTON_TIGHT) && (t.y > 0.0f);
+        v0 = (r2u.x < s.thr_strict) & (fabsf(ft_last.x) < NEWTON_TIGHT) & (t.x > 0.0f);            // surfaces.py:584
+        v1 = (r2u.y < s.thr_strict) & (fabsf(ft_last.y) < NEWTON_TIGHT) & (t.y > 0.0f);
         f2 g, dg;
         sag_slope_strict2<K, NAI, false>(s, r2u, g, dg);                                      // (x, y masked by ra > 0: alive here)
         const f2 dg2 = mul2s(dg, bc2(2.0f));
@@ -292,12 +293,16 @@ static bool strict_loop_ok(const LensDev &L) {
         const SurfDev &s = L.s[j];
         if (s.kind != SDIRT_SURF_FLAT && s.fixed_iters >= 0) return false;
         if (s.kind == SDIRT_SURF_ASPHERE && !(s.n_ai == 0 || (s.n_ai >= 4 && s.n_ai <= 6))) return false;
+        if (s.kind == SDIRT_SURF_ASPHERE && !(s.flags & F_KGT)) return false;        // k <= -1: the loose mask is not an upper bound
     }
     return true;
 }
 
 #ifndef SDIRT_STRICT_BLOCK
 #define SDIRT_STRICT_BLOCK 16
+#endif
+#ifndef SDIRT_STRICT_THREADS
+#define SDIRT_STRICT_THREADS 256
 #endif
 #ifndef SDIRT_STRICT_MIN_CTAS
 #define SDIRT_STRICT_MIN_CTAS 4       // 256-thread CTAs per SM: 64 registers per thread (measured 2 % faster than 3 x 80 despite ~200 B of spills)
@@ -307,6 +312,7 @@ struct TraceStrictLoop {
     static constexpr bool ONE_RAY_LOOP = false;      // no one-ray variant of the loop in this kernel (the generic kernel is the comparison)
     static constexpr bool STRICT_SPLAT = true;
     static constexpr int MIN_CTAS = SDIRT_STRICT_MIN_CTAS;
+    static constexpr int THREADS = SDIRT_STRICT_THREADS;   // (its interleaved blocks do not need chunk / threads to be whole)
     static constexpr int BLOCK = SDIRT_STRICT_BLOCK;     // samples per lane and block of the interleaved assignment (fast_path.cuh)
     static __device__ __forceinline__ bool trace(const LensDev &L, RayReg &r, bool) {      // one-ray loop (debug switch): the generic strict trace
         trace_lens<STRICT, false>(L, r, nullptr, 0, 0, false);
