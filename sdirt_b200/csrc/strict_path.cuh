@@ -55,6 +55,7 @@ __device__ __forceinline__ void poly_terms2(const SurfDev &s, f2 r2, f2 &g, f2 &
 // sequence (div_rn2) spends two more operations refining the reciprocal first; every instruction of this kernel costs issue
 // slots (a packed instruction takes two, tools/probe/issue_mix_probe.cu), and the reference's own CPU arithmetic is further from
 // IEEE than this (MKL's vector sqrt is off by one ulp for 0.6 % of its inputs, tests/test_oracle_golden.py).
+struct StrictWatch { float kmax, smax; };       // see newton_eval2
 #ifndef SDIRT_STRICT_SHORT_DIV
 #define SDIRT_STRICT_SHORT_DIV 1
 #endif
@@ -85,10 +86,11 @@ __device__ __forceinline__ void sdiv2x3(f2 a0, f2 a1, f2 a2, f2 b, f2 &q0, f2 &q
 
 // sag G(rho^2) and slope G'(rho^2) (sag_and_slope in engine.cu) on each half; the square root is shared.
 // (r2 c2) / 2 is taken as r2 (c2 / 2): scaling by a power of two commutes with rounding.
-template <int KIND, int NAI, bool WANT_G>
-__device__ __forceinline__ void sag_slope_strict2(const SurfDev &s, f2 r2, f2 &g, f2 &dg) {
+template <int KIND, int NAI, bool WANT_G, bool WATCH>
+__device__ __forceinline__ void sag_slope_strict2(const SurfDev &s, f2 r2, f2 &g, f2 &dg, StrictWatch &w) {
     // ((1 + k) r2) c2; with k = 0 (spheres, and aspheres whose conic constant is zero) the first product is r2 itself
     const f2 kr2c2 = (KIND == SIG_SPHERE || (s.flags & F_KZERO)) ? mul2s(r2, bc2(s.c2)) : mul2s(mul2s(bc2(s.onek), r2), bc2(s.c2));
+    if (WATCH) w.kmax = fmaxf(fmaxf(kr2c2.x, kr2c2.y), w.kmax);
 #if SDIRT_STRICT_SHORT_DIV
     // sqrt_rn2 keeping its MUFU.RSQ seed y ~ 1 / sf (2^-22) as the reciprocal of the quotient by sf.  The reference's term is
     // ((r2 c2) / 2) / sf; TWICE that, (r2 c2) / sf, is the same quotient up to the exact scaling, and the halving rides in the
@@ -120,23 +122,32 @@ __device__ __forceinline__ void sag_slope_strict2(const SurfDev &s, f2 r2, f2 &g
     if constexpr (KIND == SIG_ASPHERE && NAI > 0) poly_terms2<NAI, WANT_G>(s, r2, g, dg);
 }
 
+// What the packed tracer leaves out of a loose evaluation, and how it knows: the mask select (an iterate outside the surface's own
+// radius of definition is evaluated at rho = 0, surfaces.py:548-552) and the +-5 mm clamp of the Newton step (surfaces.py:558-560)
+// cost eight instructions per evaluation pair and act on essentially no ray of a real lens.  Instead two running maxima ride along
+// through the whole lens -- kmax over (1 + k) rho^2 c^2 of every loose evaluation (the mask acts where that reaches 1 up to a few
+// ulp), smax over |step| of every evaluation -- one three-input FMNMX3 each, which returns the non-NaN operands (a dead, NaN half
+// never shows).  A pair that ends the lens with kmax >= STRICT_KMAX or smax > 5 mm is traced again, ray by ray, with the
+// generic strict tracer (retrace_pair_general): for every other pair the evaluations below ARE the reference's arithmetic.
+#define STRICT_KMAX 0.99999f
+
 // One Newton evaluation (surfaces.py:548-561 / 569-578) at t for both halves: the residual and the updated t.
-// STRICT selects the mask of the one extra evaluation after the loop (_valid) instead of the loop's (_valid_loose).
+// STRICT: the one extra evaluation after the loop (_valid instead of _valid_loose); it keeps its mask select, because rays stopped
+// by a surface's clear aperture are not rare.
 template <int KIND, int NAI, bool STRICT>
-__device__ __forceinline__ void newton_eval2(const SurfDev &s, const Ray2 &r, f2 a, f2 b, f2 t, f2 &ftn, f2 &tn) {
+__device__ __forceinline__ void newton_eval2(const SurfDev &s, const Ray2 &r, f2 a, f2 b, f2 t, f2 &ftn, f2 &tn, StrictWatch &w) {
     const f2 nx = add2(r.ox, mul2s(r.dx, t)), ny = add2(r.oy, mul2s(r.dy, t)), nz = add2(r.oz, mul2s(r.dz, t));
     const f2 r2u = add2(mul2s(nx, nx), mul2s(ny, ny));
     // k > -1 (every surface this tracer accepts, strict_loop_ok): both masks are upper bounds on rho^2
-    const float thr = STRICT ? s.thr_strict : s.bound;
-    const bool m0 = r2u.x < thr, m1 = r2u.y < thr;
-    const f2 r2 = make_float2(m0 ? r2u.x : 0.0f, m1 ? r2u.y : 0.0f);
+    f2 r2 = r2u;
+    if (STRICT) r2 = make_float2(r2u.x < s.thr_strict ? r2u.x : 0.0f, r2u.y < s.thr_strict ? r2u.y : 0.0f);
     f2 g, dg;
-    sag_slope_strict2<KIND, NAI, true>(s, r2, g, dg);
+    sag_slope_strict2<KIND, NAI, true, !STRICT>(s, r2, g, dg, w);
     ftn = add2(add2(g, bc2(s.d)), neg2(nz));
     // -(f' + eps) instead of f' + eps (rounding is symmetric under negation): no negated copy of d_z is needed as an FMA addend
     const f2 ndf = add2(fma2(bc2(-2.0f), mul2s(dg, add2(mul2s(a, t), b)), r.dz), bc2(-EPS_F));
-    f2 nstep = sdiv2(ftn, ndf);
-    nstep = make_float2(fminf(fmaxf(nstep.x, -NEWTON_STEP), NEWTON_STEP), fminf(fmaxf(nstep.y, -NEWTON_STEP), NEWTON_STEP));
+    const f2 nstep = sdiv2(ftn, ndf);
+    w.smax = fmaxf(fmaxf(fabsf(nstep.x), fabsf(nstep.y)), w.smax);
     tn = add2(t, nstep);
 }
 
@@ -146,8 +157,10 @@ __device__ __forceinline__ void newton_eval2(const SurfDev &s, const Ray2 &r, f2
 // t -> t_new ends in a fixed point or a 2-cycle long before the residual test is met; both are detected and the rest of the
 // loop is skipped with its known outcome (newton_strict in engine.cu does the same).  Without FIRST the same rays simply run to
 // the cap: same result, more evaluations.
+// (Splitting the loop into "both halves iterating", without the selects on t, plus a loop for the stragglers saves three more
+// instructions per evaluation and loses more than that to warps whose threads sit in different loops: profiles/r02n_*.)
 template <int KIND, int NAI, bool FIRST>
-__device__ __forceinline__ void newton_strict2(const SurfDev &s, const Ray2 &r, f2 &t_out, f2 &ft_last) {
+__device__ __forceinline__ void newton_strict2(const SurfDev &s, const Ray2 &r, f2 &t_out, f2 &ft_last, StrictWatch &w) {
     const f2 t0 = sdiv2(add2(bc2(s.d), neg2(r.oz)), r.dz);
     const f2 a = add2(mul2s(r.dx, r.dx), mul2s(r.dy, r.dy));
     const f2 b = add2(mul2s(r.dx, r.ox), mul2s(r.dy, r.oy));
@@ -158,7 +171,7 @@ __device__ __forceinline__ void newton_strict2(const SurfDev &s, const Ray2 &r, 
 #pragma unroll 1
     do {
         f2 ftn, tn;
-        newton_eval2<KIND, NAI, false>(s, r, a, b, t, ftn, tn);
+        newton_eval2<KIND, NAI, false>(s, r, a, b, t, ftn, tn, w);
         ++it;
         if (FIRST && it >= 3) {
             // period 1 (t_new == t): every further evaluation repeats this one.  period 2 (t_new == the t before this
@@ -183,17 +196,15 @@ __device__ __forceinline__ void newton_strict2(const SurfDev &s, const Ray2 &r, 
         }
     } while ((run0 || run1) && it < NEWTON_MAXIT);
     t = add2(t0, add2(t, neg2(t0)));                                               // surfaces.py:563-567
-    newton_eval2<KIND, NAI, true>(s, r, a, b, t, ft_last, t_out);
+    newton_eval2<KIND, NAI, true>(s, r, a, b, t, ft_last, t_out, w);
 }
 
-// Snell (surfaces.py:633-679, forward direction) for a pair, given q = the unit normal up to the sign `sigma` the reference
-// gives it (n = sigma q): cos_i = sigma (d.q), and in d' = sr n + eta (d - cos_i n) the sign survives only on the sr term.
-__device__ __forceinline__ void refract_strict2(const SurfDev &s, Ray2 &r, f2 qx, f2 qy, f2 qz, float sigma, bool &v0, bool &v1) {
+// The two validity tests of the step (cos_i^2 > 0.1, no total internal reflection: e < 1) are left to the caller, which folds them
+// into the surface's own tests (kill_* below).
+__device__ __forceinline__ void refract_strict2(const SurfDev &s, Ray2 &r, f2 qx, f2 qy, f2 qz, float sigma, f2 &c2, f2 &e) {
     const f2 cq = add2(add2(mul2s(r.dx, qx), mul2s(r.dy, qy)), mul2s(r.dz, qz));
-    const f2 c2 = mul2s(cq, cq);
-    const f2 e = mul2s(bc2(s.eta2), add2(bc2(1.0f), neg2(c2)));
-    v0 = v0 & (c2.x > 0.1f) & (e.x < 1.0f);          // (plain conjunctions: one select on the combined predicate, not one per test)
-    v1 = v1 & (c2.y > 0.1f) & (e.y < 1.0f);
+    c2 = mul2s(cq, cq);
+    e = mul2s(bc2(s.eta2), add2(bc2(1.0f), neg2(c2)));
     const f2 sr = mul2(bc2(sigma), sqrt_rn2(add2(bc2(1.0f), neg2(e))));
     r.dx = add2(mul2s(sr, qx), mul2s(bc2(s.eta), add2(r.dx, neg2(mul2s(cq, qx)))));
     r.dy = add2(mul2s(sr, qy), mul2s(bc2(s.eta), add2(r.dy, neg2(mul2s(cq, qy)))));
@@ -208,12 +219,37 @@ __device__ __forceinline__ void strict_kill2(Ray2 &r, bool v0, bool v1) {
     const float nan = __int_as_float(0x7fc00000);
     r.dz = make_float2(v0 ? r.dz.x : nan, v1 ? r.dz.y : nan);
 }
+// The conjunction of a surface's validity tests as ONE predicate chain (setp.and) and one select per half: written out in C the
+// compiler keeps one select per test (six FSEL per pair and surface instead of two).  0f3DCCCCCD = 0.1f, 0f7FC00000 = NaN.
+// sphere, surfaces.py:464 + 667-669:  rho^2 <= r^2, t >= 0, cos^2 > 0.1, e < 1
+__device__ __forceinline__ float kill_sphere(float dz, float r2u, float r2, float t, float c2, float e) {
+    float out;
+    asm("{ .reg .pred p;\n\t"
+        "setp.le.f32 p, %2, %3;\n\t"
+        "setp.ge.and.f32 p, %4, 0f00000000, p;\n\t"
+        "setp.gt.and.f32 p, %5, 0f3DCCCCCD, p;\n\t"
+        "setp.lt.and.f32 p, %6, 0f3F800000, p;\n\t"
+        "selp.f32 %0, %1, 0f7FC00000, p; }" : "=f"(out) : "f"(dz), "f"(r2u), "f"(r2), "f"(t), "f"(c2), "f"(e));
+    return out;
+}
+// asphere, surfaces.py:584 + 667-669:  rho^2 < thr, |ft| < 10e-6, t > 0, cos^2 > 0.1, e < 1
+__device__ __forceinline__ float kill_asphere(float dz, float r2u, float thr, float ft, float t, float c2, float e) {
+    float out;
+    asm("{ .reg .pred p;\n\t"
+        "setp.lt.f32 p, %2, %3;\n\t"
+        "setp.lt.and.f32 p, %4, 0f3727C5AC, p;\n\t"
+        "setp.gt.and.f32 p, %5, 0f00000000, p;\n\t"
+        "setp.gt.and.f32 p, %6, 0f3DCCCCCD, p;\n\t"
+        "setp.lt.and.f32 p, %7, 0f3F800000, p;\n\t"
+        "selp.f32 %0, %1, 0f7FC00000, p; }" : "=f"(out) : "f"(dz), "f"(r2u), "f"(thr), "f"(fabsf(ft)), "f"(t), "f"(c2), "f"(e));
+    return out;
+}
 
 // Aspheric.ray_reaction (surfaces.py:391-520) for one surface of kind K (SIG_STOP covers every flat surface: whether it refracts
 // is a run-time flag) and a pair of rays; r.oz is ABSOLUTE here (the reference's coordinates), unlike the fast tracer's
 // vertex-relative z.  A dead half carries garbage that nothing reads.
 template <int K, int NAI, bool FIRST>
-__device__ __forceinline__ void strict_step2(const SurfDev &s, Ray2 &r) {
+__device__ __forceinline__ void strict_step2(const SurfDev &s, Ray2 &r, StrictWatch &w) {
     if (K == SIG_STOP) {
         const f2 t = sdiv2(add2(bc2(s.d), neg2(r.oz)), r.dz);
         r.ox = add2(r.ox, mul2s(t, r.dx)); r.oy = add2(r.oy, mul2s(t, r.dy)); r.oz = add2(r.oz, mul2s(t, r.dz));
@@ -226,48 +262,50 @@ __device__ __forceinline__ void strict_step2(const SurfDev &s, Ray2 &r) {
             v0 = r2u.x <= s.r2_sqrt_le;                                                      // sqrt(x^2 + y^2) <= r, surfaces.py:421
             v1 = r2u.y <= s.r2_sqrt_le;
         }
-        if (s.flags & F_REFRACTS) refract_strict2(s, r, bc2(0.0f), bc2(0.0f), bc2(1.0f), 1.0f, v0, v1);   // n = -normalize((0,0,-1))
+        if (s.flags & F_REFRACTS) {
+            f2 c2, e;
+            refract_strict2(s, r, bc2(0.0f), bc2(0.0f), bc2(1.0f), 1.0f, c2, e);                      // n = -normalize((0,0,-1))
+            v0 = v0 & (c2.x > 0.1f) & (e.x < 1.0f);
+            v1 = v1 & (c2.y > 0.1f) & (e.y < 1.0f);
+        }
         strict_kill2(r, v0, v1);
         return;
     }
     f2 t, ft_last;
-    newton_strict2<K, NAI, FIRST>(s, r, t, ft_last);
+    newton_strict2<K, NAI, FIRST>(s, r, t, ft_last, w);
     r.ox = add2(r.ox, mul2s(t, r.dx)); r.oy = add2(r.oy, mul2s(t, r.dy)); r.oz = add2(r.oz, mul2s(t, r.dz));
     const f2 r2u = add2(mul2s(r.ox, r.ox), mul2s(r.oy, r.oy));
-    bool v0, v1;
-    f2 qx, qy, qz;
+    f2 qx, qy, qz, c2, e;
     if (K == SIG_SPHERE) {
-        v0 = (r2u.x <= s.r2) & (t.x >= 0.0f);                                                // surfaces.py:464
-        v1 = (r2u.y <= s.r2) & (t.y >= 0.0f);
         // gradient (+-2x, +-2y, +-(2z - 2(d+R))) = +-2 (x, y, w): the normalised vector is +-(x, y, w) / |(x, y, w)| bit for bit
         const f2 w = add2(r.oz, bc2(-s.dR));
         const f2 nrm = sqrt_rn2(fma2(w, w, fma2(r.oy, r.oy, mul2s(r.ox, r.ox))));             // norm3
         sdiv2x3(r.ox, r.oy, w, nrm, qx, qy, qz);
-        refract_strict2(s, r, qx, qy, qz, s.sigma, v0, v1);
+        refract_strict2(s, r, qx, qy, qz, s.sigma, c2, e);
+        r.dz = make_float2(kill_sphere(r.dz.x, r2u.x, s.r2, t.x, c2.x, e.x), kill_sphere(r.dz.y, r2u.y, s.r2, t.y, c2.y, e.y));
     } else {
-        v0 = (r2u.x < s.thr_strict) & (fabsf(ft_last.x) < NEWTON_TIGHT) & (t.x > 0.0f);            // surfaces.py:584
-        v1 = (r2u.y < s.thr_strict) & (fabsf(ft_last.y) < NEWTON_TIGHT) & (t.y > 0.0f);
         f2 g, dg;
-        sag_slope_strict2<K, NAI, false>(s, r2u, g, dg);                                      // (x, y masked by ra > 0: alive here)
+        sag_slope_strict2<K, NAI, false, false>(s, r2u, g, dg, w);                                      // (x, y masked by ra > 0: alive here)
         const f2 dg2 = mul2s(dg, bc2(2.0f));
         const f2 gx = mul2s(dg2, r.ox), gy = mul2s(dg2, r.oy);
         const f2 nrm = sqrt_rn2(add2(fma2(gy, gy, mul2s(gx, gx)), bc2(1.0f)));               // norm3(gx, gy, -1)
         sdiv2x3(gx, gy, bc2(-1.0f), nrm, qx, qy, qz);
-        refract_strict2(s, r, qx, qy, qz, -1.0f, v0, v1);
+        refract_strict2(s, r, qx, qy, qz, -1.0f, c2, e);
+        r.dz = make_float2(kill_asphere(r.dz.x, r2u.x, s.thr_strict, ft_last.x, t.x, c2.x, e.x),
+                           kill_asphere(r.dz.y, r2u.y, s.thr_strict, ft_last.y, t.y, c2.y, e.y));
     }
-    strict_kill2(r, v0, v1);
 }
 
 // One surface of any kind.  Polynomial orders compiled: 0 (pure conic), 4, 5, 6 coefficients; the cycle detection of the first
 // surface is compiled for spheres only (any other first surface takes the plain loop: same result).
 template <bool FIRST>
-__device__ __forceinline__ void strict_surface2(const SurfDev &s, Ray2 &r) {
-    if (s.kind == SDIRT_SURF_SPHERE) strict_step2<SIG_SPHERE, 0, FIRST>(s, r);
-    else if (s.kind == SDIRT_SURF_FLAT) strict_step2<SIG_STOP, 0, false>(s, r);
-    else if (s.n_ai == 6) strict_step2<SIG_ASPHERE, 6, false>(s, r);
-    else if (s.n_ai == 0) strict_step2<SIG_ASPHERE, 0, false>(s, r);
-    else if (s.n_ai == 4) strict_step2<SIG_ASPHERE, 4, false>(s, r);
-    else strict_step2<SIG_ASPHERE, 5, false>(s, r);
+__device__ __forceinline__ void strict_surface2(const SurfDev &s, Ray2 &r, StrictWatch &w) {
+    if (s.kind == SDIRT_SURF_SPHERE) strict_step2<SIG_SPHERE, 0, FIRST>(s, r, w);
+    else if (s.kind == SDIRT_SURF_FLAT) strict_step2<SIG_STOP, 0, false>(s, r, w);
+    else if (s.n_ai == 6) strict_step2<SIG_ASPHERE, 6, false>(s, r, w);
+    else if (s.n_ai == 0) strict_step2<SIG_ASPHERE, 0, false>(s, r, w);
+    else if (s.n_ai == 4) strict_step2<SIG_ASPHERE, 4, false>(s, r, w);
+    else strict_step2<SIG_ASPHERE, 5, false>(s, r, w);
 }
 
 // The whole lens as a run-time loop over the resolved surfaces: ONE copy of the sphere / flat / asphere code (plus the first
@@ -275,15 +313,31 @@ __device__ __forceinline__ void strict_surface2(const SurfDev &s, Ray2 &r) {
 // ~1000 executed instructions per ray pair in this arithmetic, so the loop's overhead is noise, while the unrolled form (4400
 // instructions for 12 surfaces, 6000 for 21) ran with `no_instruction` among its first stall reasons (profiles/r02b_*): the
 // strict kernel is the one place where the run-time loop wins.
-__device__ __forceinline__ void trace_strict_loop2(const LensDev &L, Ray2 &r) {
-    strict_surface2<true>(L.s[0], r);
+// Returns whether the pair has to be traced again with the generic tracer (see newton_eval2).
+__device__ __forceinline__ bool trace_strict_loop2(const LensDev &L, Ray2 &r) {
+    StrictWatch w = {0.0f, 0.0f};
+    strict_surface2<true>(L.s[0], r, w);
 #pragma unroll 1
     for (int j = 1; j < L.n; ++j) {
         if (r.dz.x != r.dz.x && r.dz.y != r.dz.y) continue;  // both halves dead (no early exit: the loop counter stays warp-uniform)
-        strict_surface2<false>(L.s[j], r);
+        strict_surface2<false>(L.s[j], r, w);
     }
     r.a0 = r.dz.x == r.dz.x;
     r.a1 = r.dz.y == r.dz.y;
+    return w.kmax >= STRICT_KMAX || w.smax > NEWTON_STEP;
+}
+
+// The rare pair: both rays through the generic one-ray strict tracer (trace_lens<STRICT> in engine.cu, the code behind
+// sdirt_trace_rays), handed back in the packed tracer's conventions (absolute z, a dead half has d_z = NaN).  Not inlined: it is
+// the whole generic surface loop, and it runs for essentially no pair.
+__device__ __noinline__ void retrace_pair_general(const LensDev &L, float px, float py, float pz, float2 s0, float2 s1, float pupil_z, float *out /*[12], local*/) {
+    RayReg r0 = ray_from_point(px, py, pz, s0.x, s0.y, pupil_z), r1 = ray_from_point(px, py, pz, s1.x, s1.y, pupil_z);
+    trace_lens<STRICT, false>(L, r0, nullptr, 0, 0, false);
+    trace_lens<STRICT, false>(L, r1, nullptr, 0, 0, false);
+    const float nan = __int_as_float(0x7fc00000);
+    out[0] = r0.ox; out[1] = r1.ox; out[2] = r0.oy; out[3] = r1.oy; out[4] = r0.oz; out[5] = r1.oz;
+    out[6] = r0.dx; out[7] = r1.dx; out[8] = r0.dy; out[9] = r1.dy;
+    out[10] = r0.alive ? r0.dz : nan; out[11] = r1.alive ? r1.dz : nan;
 }
 
 // can the packed strict tracer take this (resolved) lens?  forward, per-ray Newton schedule, compiled polynomial orders
@@ -321,7 +375,13 @@ struct TraceStrictLoop {
     static __device__ __forceinline__ float sensor_distance(const LensDev &L, const RayReg &r) { return L.d_sensor - r.oz; }
     static __device__ __forceinline__ Ray2 trace2(const LensDev &L, float px, float py, float pz, float2 s0, float2 s1, float pupil_z, bool) {
         Ray2 r = ray2_from_point(px, py, pz, s0, s1, pupil_z);
-        trace_strict_loop2(L, r);
+        if (trace_strict_loop2(L, r) || L.debug_scalar_strict == 3) {   // (3: testing aid, every pair takes the rare path; the ray itself stays in registers: only this branch goes through memory)
+            float buf[12];
+            retrace_pair_general(L, px, py, pz, s0, s1, pupil_z, buf);
+            r.ox = make_float2(buf[0], buf[1]); r.oy = make_float2(buf[2], buf[3]); r.oz = make_float2(buf[4], buf[5]);
+            r.dx = make_float2(buf[6], buf[7]); r.dy = make_float2(buf[8], buf[9]); r.dz = make_float2(buf[10], buf[11]);
+            r.a0 = r.dz.x == r.dz.x; r.a1 = r.dz.y == r.dz.y;
+        }
         return r;
     }
 };

@@ -132,10 +132,17 @@ class Lensgroup(DeepObj):
         """Shared pupil disc samples, CPU generator, theta first then rho^2 (optics.py:482-487).  `spatial_order`
         returns the same set Morton-sorted on the device (a PSF is a sum over the set, so its order is free)."""
         pupilz, pupilr = self.entrance_pupil(shrink_pupil=shrink_pupil)
-        theta = torch.rand(spp) * 2 * np.pi
-        r = torch.sqrt(torch.rand(spp) * pupilr ** 2)
-        xy = torch.stack((r * torch.cos(theta), r * torch.sin(theta)), 1)
-        xy = xy.to(self.device, non_blocking=True).contiguous()
+        if getattr(self, "sample_rng", "cpu") == "cuda":
+            # engine extension: the same two uniform draws from the DEVICE generator (torch.cuda.manual_seed), no host RNG and no
+            # 8 B / sample upload per call -- for throughput runs; seeded comparisons with the reference need the default
+            theta = torch.rand(spp, device=self.device) * 2 * np.pi
+            r = torch.sqrt(torch.rand(spp, device=self.device) * pupilr ** 2)
+            xy = torch.stack((r * torch.cos(theta), r * torch.sin(theta)), 1).contiguous()
+        else:
+            theta = torch.rand(spp) * 2 * np.pi
+            r = torch.sqrt(torch.rand(spp) * pupilr ** 2)
+            xy = torch.stack((r * torch.cos(theta), r * torch.sin(theta)), 1)
+            xy = xy.to(self.device, non_blocking=True).contiguous()
         if spatial_order:
             xy = E.pupil_sort(xy, pupilr)
         return xy, pupilz

@@ -895,3 +895,41 @@ def test_strict_bank_specialised_vs_generic(name):
     Lu, Ru, cu_ = E.psf_bank(h, 0.589, pts, pup, pz, centre, 21, 0.046875, numerics="strict", normalise=0, want_counts=True)
     assert torch.equal(cu_, cg)
     assert l1_sumnorm(Lu.cpu().numpy(), Lg.cpu().numpy()).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["rf50mm", "rf35mm"])
+def test_strict_pair_tracer_rare_path(name):
+    """The packed strict tracer leaves the loose-mask select and the +-5 mm step clamp out of its evaluations and traces a pair
+    again with the generic one-ray tracer when its running maxima say one of them would have acted (csrc/strict_path.cuh,
+    newton_eval2).  (a) With every pair forced through that path (SDIRT_DEBUG_SCALAR_STRICT=3) the sensor-plane states are the
+    same bits as without.  (b) A wide-open pupil (four times the F/4 radius: marginal rays meet the strongly curved front
+    surfaces where Newton steps exceed the clamp, and most die on the apertures) is still bit-identical to sdirt_trace_rays."""
+    import os
+    from sdirt_b200 import _engine as E
+    h = engine_lens(name)
+    pz, pr = {"rf50mm": (22.51324462890625, 6.019352912902832), "rf35mm": (14.338210105895996, 4.767455577850342)}[name]
+    g = torch.Generator().manual_seed(11)
+    m = 60001
+    ds = D_SENSOR[name]
+    for scale, pts in ((1.0, [[0.0, 0.0, -2000 + ds], [250.0, -160.0, -999.0 + ds]]), (4.0, [[0.0, 0.0, -300 + ds], [150.0, -90.0, -1500.0 + ds]])):
+        th = torch.rand(m, generator=g) * 2 * np.pi
+        rr = torch.sqrt(torch.rand(m, generator=g) * (pr * scale) ** 2)
+        pup = torch.stack([rr * torch.cos(th), rr * torch.sin(th)], -1).to(DEV).contiguous()
+        for pt in pts:
+            p = torch.tensor(pt, device=DEV)
+            got = E.debug_trace_strict2(h, 0.589, p, pup, pz)
+            try:
+                os.environ["SDIRT_DEBUG_SCALAR_STRICT"] = "3"
+                forced = E.debug_trace_strict2(h, 0.589, p, pup, pz)
+            finally:
+                os.environ.pop("SDIRT_DEBUG_SCALAR_STRICT", None)
+            assert torch.equal(got.view(torch.int32), forced.view(torch.int32)), (scale, pt)
+            o, d = E.sample_rays(p.reshape(1, 3), pup, pz)
+            o, d = o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
+            ra = torch.ones(m, device=DEV)
+            E.trace_rays(h, 0.589, o, d, ra, to_sensor=True, newton="per_ray", numerics="strict")
+            want = torch.cat([o, d, ra[:, None]], -1)
+            assert torch.equal(got[:, 6], want[:, 6]), (scale, pt, int((got[:, 6] != want[:, 6]).sum()))
+            keep = want[:, 6] > 0
+            assert int(keep.sum()) > 100, (scale, pt)
+            assert torch.equal(got[keep].view(torch.int32), want[keep].view(torch.int32)), (scale, pt)
