@@ -17,10 +17,25 @@ def available():
     return os.path.isfile(os.path.join(REF, "deeplens", "optics.py"))
 
 
-def _stub(name, **attrs):
-    m = types.ModuleType(name)
-    m.__dict__.update(attrs)
+class _Stub(types.ModuleType):
+    """An absent plotting / metric module: any attribute is a callable that must not be reached on the timed path."""
+
+    def __getattr__(self, item):
+        if item.startswith("__"):
+            raise AttributeError(item)
+
+        def _absent(*a, **k):
+            raise RuntimeError(f"{self.__name__}.{item} is a stub: this module is not installed and not on the hot path")
+        return _absent
+
+
+def _stub(name):
+    m = _Stub(name)
+    m.__path__ = []                     # lets `import a.b` resolve sub-modules registered the same way
     sys.modules[name] = m
+    parent, _, leaf = name.rpartition(".")
+    if parent in sys.modules:
+        setattr(sys.modules[parent], leaf, m)
     return m
 
 
@@ -29,22 +44,25 @@ def import_reference():
     mod = sys.modules.get("deeplens")
     if mod is not None and os.path.abspath(getattr(mod, "__file__", "")).startswith(REF):
         return mod
-    for n in ("matplotlib", "matplotlib.pyplot", "lpips", "imageio", "skimage", "skimage.io", "skimage.filters", "skimage.morphology"):
+    for n in ("matplotlib", "matplotlib.pyplot", "lpips", "imageio", "skimage", "skimage.io", "skimage.filters", "skimage.morphology",
+              "skimage.metrics"):
         if n not in sys.modules:
             try:
                 __import__(n)
             except Exception:
                 _stub(n)
-    if "skimage.metrics" not in sys.modules:
-        _stub("skimage.metrics", peak_signal_noise_ratio=None, structural_similarity=None)
-    mp = sys.modules["matplotlib"]
-    if not hasattr(mp, "pyplot"):
-        mp.pyplot = sys.modules["matplotlib.pyplot"]
     if REF not in sys.path:
         sys.path.insert(0, REF)
     import deeplens
     assert os.path.abspath(deeplens.__file__).startswith(REF), deeplens.__file__
     return deeplens
+
+
+def make_basenet(device):
+    """The reference's DfDP network (dfdp/basenet.py:9-21), random weights: the consumer of the generated focal stacks."""
+    import_reference()
+    from dfdp.basenet import Basenet
+    return Basenet("dfdp").to(device)
 
 
 def lens_json(name):

@@ -480,27 +480,51 @@ def run_gpu(args):
         t = max_over_ranks(e0.elapsed_time(e1))
         render_sharded = {"metric": "pixels/s, PSFNet.render of 16 x 3 x 1024 x 1536 (NYUv2-shaped RGB-D batch), images sharded over the ranks, no exchange",
                           "value": rb * rh * rw / (t * 1e-3), "unit": "pixels/s", "ms": t, "images_per_rank": nloc, "scaling": "strong"}
-        # FlyingThings3D-FS shape (540 x 960), a DfDP batch of 4 scenes per rank: all-in-focus image + depth -> dual-pixel training
-        # image with gamma + noise + clip (2_dfdp_net.py:161-185), weak scaling (every rank generates its own batch)
-        fh, fw, fb = 540, 960, 4
+        # The DfDP training step's data side (configs/dfdp_by_sdirt_rf50mm.yml: res 512 x 768, bs 4, n_stack 1): all-in-focus image + depth
+        # -> dual-pixel training images with gamma + noise + clip (2_dfdp_net.py:161-173), then the reference's own DfDP network consumes
+        # the batch (dfdp/basenet.py:18-49, forward incl. its losses).  Weak scaling: every rank generates and consumes its own batch.
+        fh, fw, fb = 512, 768, 4
         flens = PSFNet(lens_file(LENS), sensor_res=(fh, fw), kernel_size=KS, device=dev)
         aif = torch.rand((fb, 3, fh, fw), device=dev, generator=g)
-        fdepth = -(torch.rand((fb, 1, fh, fw), device=dev, generator=g) * 9000 + 300)
+        low = torch.rand((fb, 1, fh // 64 + 2, fw // 64 + 2), device=dev, generator=g)
+        depth_m = torch.nn.functional.interpolate(low, size=(fh, fw), mode="bilinear", align_corners=False) * 9.0 + 0.3     # metres
         ffoc = torch.full((fb,), -1000.0, device=dev)
-        flens.render_focal_stack(aif, fdepth, ffoc, train=True)
+        flens.render_focal_stack(aif, -depth_m * 1e3, ffoc, train=True)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        stack = flens.render_focal_stack(aif, fdepth, ffoc, train=True)
+        stack = flens.render_focal_stack(aif, -depth_m * 1e3, ffoc, train=True)
         e1.record()
         barrier()
         t = max_over_ranks(e0.elapsed_time(e1))
-        datagen = {"metric": "dual-pixel training images / s, render_focal_stack(train=True) at 540 x 960 (FlyingThings3D-FS shape), 4 scenes per rank",
-                   "value": world * fb / (t * 1e-3), "unit": "images/s", "ms_per_batch": t, "scaling": "weak",
-                   "dfdp_net": "the DfDP depth network (dfdp/basenet.py) is outside SURVEY section 8 and is not part of this engine; the "
-                               "generated batch [4, 6, 540, 960] is what 2_dfdp_net.py:174-185 feeds it"}
+        datagen = {"metric": "dual-pixel training images / s, render_focal_stack(train=True) at 512 x 768 (the DfDP config's resolution), 4 scenes per rank",
+                   "value": world * fb / (t * 1e-3), "unit": "images/s", "ms_per_batch": t, "scaling": "weak"}
+        try:                                                            # the consumer: the UNMODIFIED reference network, when it travelled
+            Rn = _ref_runner()
+            if Rn is None:
+                raise RuntimeError("baseline/_ref absent")
+            net = Rn.make_basenet(dev)
+            net.train()
+            feed = {"gt_depth": depth_m.clone(), "AiF_img": aif, "stack_rgb_img": stack}
+            with torch.no_grad():
+                net(feed)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                stack = flens.render_focal_stack(aif, -depth_m * 1e3, ffoc, train=True)
+                feed["stack_rgb_img"], feed["gt_depth"] = stack, depth_m.clone()
+                losses, _ = net(feed)
+                e1.record()
+                barrier()
+            t2 = max_over_ranks(e0.elapsed_time(e1))
+            datagen["with_dfdp_forward"] = {"ms_per_batch": t2, "images_per_s": world * fb / (t2 * 1e-3), "generation_share": t / t2,
+                                            "loss_depth_est": float(losses["depth_est"]),
+                                            "note": "generation + the reference's Basenet('dfdp') forward with its losses (dfdp/basenet.py), autocast as the reference decorates it"}
+            del net
+        except Exception as ex:
+            datagen["with_dfdp_forward"] = {"unavailable": repr(ex)[:300]}
         assert torch.isfinite(stack).all() and torch.isfinite(out).all()
-        del img, depth, out, aif, fdepth, stack, flens
+        del img, depth, out, aif, depth_m, stack, flens
 
     if rank != 0:
         if world > 1:
