@@ -206,6 +206,12 @@ int sdirt_render_local_psf(const float *img_dev, const void *psf_dev, int psf_is
                            int B, int C, int H, int W, int ks, int tone,
                            float *out_l_dev, float *out_r_dev, void *stream);
 
+/* local_dp_psf_render (deeplens/render_psf.py:157-188): the one variant of the three the reference runs in the INPUT's dtype --
+ * float32 image, float32 kernels, float32 products and sums, nothing rounded to half.  img[B,C,H,W], psf[B,H,W,2,ks,ks],
+ * outputs [B,C,H,W], all float32. */
+int sdirt_render_local_psf_f32(const float *img_dev, const float *psf_dev, int B, int C, int H, int W, int ks,
+                               float *out_l_dev, float *out_r_dev, void *stream);
+
 /* The same for a window of rows [row0, row0 + n_rows) of every image: psf_rows_dev is [B, n_rows, W, 2, ks, ks] (the
  * kernels of those rows only), img and the outputs are the whole [B,C,H,W] tensors (the window's halo rows are read
  * from img, replicate padding applies at the IMAGE border only).  PSFNet.render walks an image in such bands so that

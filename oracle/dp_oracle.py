@@ -713,6 +713,28 @@ def splat_points(ray: RayBundle, ps, ks, centre=None, params=None):
     return L, R
 
 
+def splat_points_f64(ray: RayBundle, ps, ks, centre, params=None):
+    """The arbiter of a summation-order dispute: the SAME float32 addends forward_integral forms for every ray (tap
+    weights and d_l / d_r exactly as splat_points computes them, monte_carlo.py:209-235), accumulated in float64 --
+    the sum the reference's sequential float32 `index_put_(accumulate=True)` and the engine's run / tile / chunk
+    summation both approximate.  Returns (L, R) as float64 [N, ks, ks]."""
+    qx, qy, w = crop_and_shift(ray, centre, ks, ps)
+    prm = DP_DEFAULT if params is None else params
+    n = ray.ox.shape[1]
+    out = np.zeros((2, n, ks, ks), np.float64)
+    one = F32(1)
+    for i in range(n):
+        x_tan = (-ray.dx[:, i]) / ray.dz[:, i]
+        r0, c0, r1, c1, wb, wr = splat_indices(qx[:, i], qy[:, i], ks, ps)
+        for side, d in enumerate(dp_weights(x_tan, prm)):
+            taps = ((r0, c0, (one - wb) * (one - wr)), (r0, c1, (one - wb) * wr), (r1, c0, wb * (one - wr)), (r0 + 1, c0 + 1, wb * wr))
+            for rr, cc, tw in taps:
+                add = ((tw * w[:, i]) * d).astype(np.float64)
+                keep = (rr >= 0) & (rr < ks) & (cc >= 0) & (cc < ks)
+                out[side, i] += np.bincount((rr * ks + cc)[keep], weights=add[keep], minlength=ks * ks).reshape(ks, ks)
+    return out[0], out[1]
+
+
 def max_normalise(psf):
     """optics.py:984-987."""
     m = psf.reshape(psf.shape[0], -1).max(-1)[:, None, None]

@@ -76,6 +76,7 @@ def lib():
     L.sdirt_splat_rays.argtypes = [vp, vp, vp, i64, i64, vp, cint, dbl, C.POINTER(DPParams), vp, vp, vp, i64, vp]
     L.sdirt_render_local_psf.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
     L.sdirt_render_local_psf_rows.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
+    L.sdirt_render_local_psf_f32.argtypes = [vp, vp, cint, cint, cint, cint, cint, vp, vp, vp]
     L.sdirt_mlp_input_layer.argtypes = [vp, vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, cint, vp, vp]
     L.sdirt_psf_pack.argtypes = [vp, i64, cint, cint, vp, vp]
     L.sdirt_mlp_fused_layout.argtypes = [C.POINTER(MlpShape), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(i64)]
@@ -115,6 +116,37 @@ def _dev(t, name, dtype=torch.float32):
 
 def _stream(t):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _on_device(fn):
+    """Run a binding with the CUDA device of its first tensor argument current: the library launches on the CURRENT device (it
+    never calls cudaSetDevice) with the stream handle taken from the tensors' device, so a call with tensors on cuda:1 while
+    cuda:0 is current would otherwise launch on the wrong device (`PSFNet(..., device='cuda:1')` in a single process)."""
+    import functools
+
+    def first_cuda(a, depth=0):
+        if isinstance(a, torch.Tensor):
+            return a.device if a.is_cuda else None
+        if isinstance(a, torch.device):
+            return a if (a.type == "cuda" and a.index is not None) else None
+        if isinstance(a, (list, tuple)) and depth < 2:
+            for x in a:
+                d = first_cuda(x, depth + 1)
+                if d is not None:
+                    return d
+        return None
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            d = first_cuda(a)
+            if d is not None:
+                if d.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(d):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapped
 
 
 def make_surface(kind, r, d, c=0.0, k=0.0, ai=None, n1=(1.0, 0.0), n2=(1.0, 0.0), square=False):
@@ -189,6 +221,7 @@ class LensHandle:
             self._h = None
 
 
+@_on_device
 def trace_rays(lens, wvln, o, d, ra, s_begin=0, s_end=None, backward=False, to_sensor=False, newton=None, record=False, numerics=None):
     """In-place trace of AoS rays o[n,3], d[n,3], ra[n]; returns the per-surface record if requested."""
     n = ra.numel()
@@ -201,6 +234,7 @@ def trace_rays(lens, wvln, o, d, ra, s_begin=0, s_end=None, backward=False, to_s
     return rec
 
 
+@_on_device
 def sample_rays(points, pupil_xy, pupil_z):
     """[spp, N, 3] origins and unit directions of sample_from_points (sample-major, as the reference's Ray)."""
     n, m = points.shape[0], pupil_xy.shape[0]
@@ -211,14 +245,17 @@ def sample_rays(points, pupil_xy, pupil_z):
     return o, d
 
 
+@_on_device
 def normalize_rays(d):
     _check(lib().sdirt_normalize_rays(_dev(d, "d"), d.numel() // 3, _stream(d)))
 
 
+@_on_device
 def propagate_rays(o, d, z):
     _check(lib().sdirt_propagate_rays(_dev(o, "o"), _dev(d, "d"), o.numel() // 3, float(z), _stream(o)))
 
 
+@_on_device
 def psf_centre(lens, wvln, points, pupil_xy, pupil_z, newton=None, numerics=None):
     n = points.shape[0]
     out = torch.empty((n, 2), device=points.device, dtype=torch.float32)
@@ -235,7 +272,9 @@ _ws_cache = {}
 
 
 def _workspace(device, nbytes):
-    key = (device.type, device.index)
+    # one scratch buffer per (device, stream): calls issued on different streams must not share partial tiles, and a buffer that
+    # is replaced by a larger one is returned to the caching allocator, which keeps it off other streams while still in flight
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes), device=device, dtype=torch.uint8)
@@ -243,6 +282,7 @@ def _workspace(device, nbytes):
     return ws
 
 
+@_on_device
 def pupil_sort(pupil_xy, radius):
     """Morton-ordered copy of the shared pupil samples [m, 2] (the order of a PSF's ray sum is free; the fused kernel's
     run-length splat is fastest when consecutive samples are neighbours in the pupil)."""
@@ -257,6 +297,7 @@ def pupil_sort(pupil_xy, radius):
     return out
 
 
+@_on_device
 def psf_bank(lens, wvln, points, pupil_xy, pupil_z, centre, ks, pixel_size, dp=None, newton=None, normalise=1,
              want_counts=False, numerics=None):
     """Fused trace + DP splat.  Returns (L [N,ks,ks], R [N,ks,ks][, valid_count [N]])."""
@@ -279,6 +320,7 @@ def psf_bank(lens, wvln, points, pupil_xy, pupil_z, centre, ks, pixel_size, dp=N
     return (out_l, out_r, cnt) if want_counts else (out_l, out_r)
 
 
+@_on_device
 def splat_rays(o, d, ra, centre, ks, pixel_size, dp=None):
     """forward_integral on an existing [spp,N] Ray: returns raw (L, R) [N,ks,ks]."""
     m, n = ra.shape
@@ -297,6 +339,7 @@ def splat_rays(o, d, ra, centre, ks, pixel_size, dp=None):
     return out_l, out_r
 
 
+@_on_device
 def tone_degamma(img, out=None):
     """PSFNet.degamma of a float32 image (any shape), elementwise; `out` may be `img`."""
     if out is None:
@@ -305,6 +348,7 @@ def tone_degamma(img, out=None):
     return out
 
 
+@_on_device
 def render_local_psf(img, psf, ks, tone=0):
     """img [B,C,H,W] float32, psf [B,H,W,2,ks,ks] float32/float16 -> (rl, rr) float32.
     tone bits: 1 = degamma the input, 2 = gamma + clip the output."""
@@ -322,6 +366,20 @@ def render_local_psf(img, psf, ks, tone=0):
     return rl, rr
 
 
+@_on_device
+def render_local_psf_f32(img, psf, ks):
+    """img [B,C,H,W] float32, psf [B,H,W,2,ks,ks] float32 -> (rl, rr) float32, float32 arithmetic throughout
+    (local_dp_psf_render, render_psf.py:157-188)."""
+    b, c, h, w = img.shape
+    if psf.dtype != torch.float32 or psf.numel() != b * h * w * 2 * ks * ks:
+        raise RuntimeError("sdirt_engine: psf must be float32 [B,H,W,2,ks,ks]")
+    rl, rr = torch.empty_like(img), torch.empty_like(img)
+    _check(lib().sdirt_render_local_psf_f32(_dev(img, "img"), _dev(psf, "psf"), b, c, h, w, int(ks), _dev(rl, "out_l"),
+                                            _dev(rr, "out_r"), _stream(img)))
+    return rl, rr
+
+
+@_on_device
 def render_local_psf_rows(img, psf_rows, ks, row0, out_l, out_r, tone=0):
     """Rows [row0, row0 + n_rows) of every image: img [B,C,H,W] float32, psf_rows [B,n_rows,W,2,ks,ks] float32/float16,
     written into the whole-image outputs out_l / out_r [B,C,H,W]."""
@@ -339,6 +397,7 @@ def render_local_psf_rows(img, psf_rows, ks, row0, out_l, out_r, tone=0):
     return out_l, out_r
 
 
+@_on_device
 def mlp_input_layer(xs, ys, z, b0, nb, row0, n_rows, w1, b1, out=None):
     """First activation of the PSF MLP for the pixels of images [b0, b0+nb), rows [row0, row0+n_rows): out [2P, n1] float16,
     row 2p = left (x, y, z), row 2p+1 = right (-x, y, z), p = ((b-b0)*n_rows + (y-row0))*W + x.  xs [W], ys [H], z [B,H,W]
@@ -358,6 +417,7 @@ def mlp_input_layer(xs, ys, z, b0, nb, row0, n_rows, w1, b1, out=None):
     return out
 
 
+@_on_device
 def psf_pack(raw, ks, out=None):
     """raw [2P, ld] float16 (ld >= ks*ks; row 2p left, 2p+1 right, unflipped) -> [P,2,ks,ks] float16 normalised kernels
     (PSFNet.pred: flip the right side, stack, divide by sum + 1e-9)."""
@@ -378,6 +438,7 @@ class FusedMlp:
     as is, every later Linear packed once into tcgen05 operand tiles.  `linears`: list of (weight [N,K], bias [N]) CUDA
     tensors in layer order, the first one being the 3 -> n1 layer."""
 
+    @_on_device
     def __init__(self, linears):
         (w1, b1), rest = linears[0], linears[1:]
         if w1.shape[1] != 3 or not rest:
@@ -404,6 +465,7 @@ class FusedMlp:
                                                     C.c_void_p(self.packed_w.data_ptr()), _dev(self.packed_b, "bias"), _stream(w16)))
         self.n_out = int(sh.N[sh.n_layers - 1])
 
+    @_on_device
     def pred(self, xs, ys, z, b0, nb, row0, n_rows, ks, out=None):
         """Normalised L/R kernels [P,2,ks,ks] float16 of the pixels of images [b0, b0+nb), rows [row0, row0+n_rows)."""
         bsz, h, w = z.shape
@@ -421,6 +483,7 @@ class FusedMlp:
         return out
 
 
+@_on_device
 def gamma_noise_clip(x, randn, noise_range, weight):
     """In place on x [N,2C,H,W] float32: clip(gamma(x) + (randn * noise_range[n]) * ramp, 0, 1); ramp = weight[n, col] for the
     left channels, weight[n, W-1-col] for the right ones (PSFNet.gamma / noise / clip of render(train=True))."""
@@ -432,12 +495,14 @@ def gamma_noise_clip(x, randn, noise_range, weight):
     return x
 
 
+@_on_device
 def fp32_peak_probe(device, blocks, threads, iters):
     out = torch.empty(blocks * threads, device=device, dtype=torch.float32)
     _check(lib().sdirt_fp32_peak_probe(_dev(out, "out"), blocks, threads, iters, _stream(out)))
     return out
 
 
+@_on_device
 def debug_trace_strict2(lens, wvln, point, pupil_xy, pupil_z):
     """Testing aid: sensor-plane states [m, 7] = (o, d, alive) of the m rays from one object point, traced by the packed strict
     tracer of the specialised parity kernel (csrc/strict_path.cuh)."""

@@ -178,6 +178,49 @@ class Lensgroup(DeepObj):
             point_source[..., 1] *= scale * self.sensor_size[1] / 2
         return point_source
 
+    @torch.no_grad()
+    def sample_pupil(self, res=(512, 512), spp=16, num_angle=8, pupilr=None, pupilz=None):
+        """Points [spp, H, W, 3] on the entrance-pupil disc: uniform, or stratified into `num_angle` sectors x spp / num_angle
+        rings when spp is small (optics.py:542-594).  The draws come from the CPU generator in the reference's order (the
+        reference draws on its own device), so a seeded run reproduces the reference's CPU run."""
+        H, W = res
+        if pupilr is None or pupilz is None:
+            pupilz, pupilr = self.entrance_pupil()
+        if spp % num_angle != 0 or spp >= 10000:
+            theta = torch.rand((spp, H, W)) * 2 * np.pi
+            r = torch.sqrt(torch.rand((spp, H, W)) * pupilr ** 2)
+            x, y = r * torch.cos(theta), r * torch.sin(theta)
+        else:
+            xs, ys = [], []
+            for i in range(num_angle):
+                for j in range(spp // num_angle):
+                    theta = torch.rand((1, H, W)) * 2 * np.pi / num_angle + i * 2 * np.pi / num_angle
+                    r2 = torch.rand((1, H, W)) * pupilr ** 2 / spp * num_angle + j * pupilr ** 2 / spp * num_angle
+                    r = torch.sqrt(r2)
+                    xs.append(r * torch.cos(theta))
+                    ys.append(r * torch.sin(theta))
+            x, y = torch.cat(xs, dim=0), torch.cat(ys, dim=0)
+        return torch.stack((x, y, torch.full_like(x, pupilz)), -1).to(self.device)
+
+    @torch.no_grad()
+    def sample_point_source(self, R=None, depth=-10.0, M=11, spp=16, fov=10.0, forward=True, pupil=True, wvln=DEFAULT_WAVE,
+                            importance_sampling=False):
+        """Forward rays [spp, M, M, 3] from an M x M grid on the plane z = depth towards per-point pupil samples
+        (optics.py:403-456); used by the spot / RMS / magnification analyses."""
+        self._require_cuda()
+        if R is None:
+            R = self.surfaces[0].r
+        Rw = R * self.sensor_res[1] / self.sensor_res[0]
+        x, y = torch.meshgrid(torch.linspace(-1, 1, M), torch.linspace(1, -1, M), indexing="xy")
+        if importance_sampling:
+            x, y = torch.sqrt(x.abs()) * x.sign(), torch.sqrt(y.abs()) * y.sign()
+        x, y = x * Rw, y * R
+        o = torch.stack((x, y, torch.full_like(x, depth)), -1).to(self.device).unsqueeze(0).repeat(spp, 1, 1, 1)
+        if not pupil:
+            raise Exception("Cone sampling specified by fov has been abandoned. Use pupil sampling instead.")
+        d = self.sample_pupil(res=(M, M), spp=spp) - o
+        return Ray(o, d, wvln, device=self.device)              # (Ray normalises d with the reference's rounding)
+
     # ==============================================================================================
     # Ray tracing (optics.py:601-717)
     # ==============================================================================================
@@ -345,6 +388,65 @@ class Lensgroup(DeepObj):
     @torch.no_grad()
     def calc_scale_pinhole(self, depth):
         return -depth * np.tan(self.hfov) / self.r_last
+
+    @torch.no_grad()
+    def calc_magnification3(self, depth):
+        """Magnification from the traced image of a 21 x 21 object grid, 512 rays per point (optics.py:1237-1272)."""
+        M, spp = 21, 512
+        ray = self.sample_point_source(M=M, spp=spp, depth=depth, R=-depth * np.tan(self.hfov) * 0.5, pupil=True)
+        o1 = torch.flip(ray.o.detach()[..., :2], [1, 2])
+        ray, _, _ = self.trace(ray)
+        o2 = ray.project_to(self.d_sensor)
+        x1 = o1[0, :, :, 0]
+        x2 = torch.sum(o2[..., 0] * ray.ra, axis=0) / torch.sum(ray.ra, axis=0).add(EPSILON)
+        tmp = (x1 / x2)[:M // 2, :M // 2]
+        mag = 1 / torch.mean(tmp[~tmp.isnan()]).item()
+        if mag == 0:
+            return 1 / (-depth * np.tan(self.hfov) / self.r_last)
+        return mag
+
+    @torch.no_grad()
+    def calc_scale_ray(self, depth):
+        """Object-to-sensor scale by ray tracing (optics.py:1310-1322)."""
+        if isinstance(depth, torch.Tensor) and len(depth.shape) == 1:
+            return torch.tensor([1 / self.calc_magnification3(d) for d in depth])
+        return 1 / self.calc_magnification3(depth)
+
+    @torch.no_grad()
+    def analysis_rms(self, depth=DEPTH, ref=True):
+        """(average, on-axis, off-axis) RMS spot radius in mm over the three design wavelengths, referred to the green
+        spot centre (optics.py:2103-2140), on a 31 x 31 field grid with GEO_SPP rays per point."""
+        H = 31
+        scale = self.calc_scale_ray(depth)
+        R = self.sensor_size[0] / 2 * scale
+        if ref:
+            ray = self.sample_point_source(M=H, spp=GEO_SPP, depth=depth, R=R, pupil=True, wvln=DEFAULT_WAVE)
+            ray, _, _ = self.trace(ray)
+            p_green = ray.project_to(self.d_sensor)
+            p_center_ref = (p_green * ray.ra.unsqueeze(-1)).sum(0) / ray.ra.sum(0).add(0.0001).unsqueeze(-1)
+        rms, rms_on_axis, rms_off_axis = [], [], []
+        for wvln in WAVE_RGB:
+            ray = self.sample_point_source(M=H, spp=GEO_SPP, depth=depth, R=R, pupil=True, wvln=wvln)
+            ray, _, _ = self.trace(ray)
+            o2 = ray.project_to(self.d_sensor)
+            o2_center = (o2 * ray.ra.unsqueeze(-1)).sum(0) / ray.ra.sum(0).add(0.0001).unsqueeze(-1)
+            o2_norm = (o2 - (p_center_ref if ref else o2_center)) * ray.ra.unsqueeze(-1)
+            rms.append(torch.sqrt(torch.sum(o2_norm ** 2 * ray.ra.unsqueeze(-1)) / torch.sum(ray.ra)))
+            rms_on_axis.append(torch.sqrt(torch.sum(o2_norm[:, H // 2 + 1, H // 2 + 1, :] ** 2 * ray.ra[:, H // 2 + 1, H // 2 + 1].unsqueeze(-1))
+                                          / torch.sum(ray.ra[:, H // 2, H // 2])))
+            rms_off_axis.append(torch.sqrt(torch.sum(o2_norm[:, 0, 0, :] ** 2 * ray.ra[:, 0, 0].unsqueeze(-1)) / torch.sum(ray.ra[:, 0, 0])))
+        return sum(rms) / len(rms), sum(rms_on_axis) / len(rms_on_axis), sum(rms_off_axis) / len(rms_off_axis)
+
+    @torch.no_grad()
+    def analysis(self, save_name="./test", ks=None, render=False, multi_plot=False, plot_invalid=True, zmx_format=False, depth=DEPTH,
+                 render_unwarp=False, lens_title=None):
+        """The numeric part of Lensgroup.analysis (optics.py:1663-1683): the RMS spot radii, printed as the reference prints
+        them and returned.  Its drawings (layout with ray paths, PSF map PNG, rendered resolution chart) are matplotlib / OpenCV
+        output outside the hot path (out of scope) and are not produced."""
+        rms_avg, rms_on, rms_off = self.analysis_rms(depth=depth)
+        print(f"On-axis RMS radius: {round(rms_on.item() * 1000, 3)}um, Off-axis RMS radius: {round(rms_off.item() * 1000, 3)}um, "
+              f"Avg RMS spot size (radius): {round(rms_avg.item() * 1000, 3)}um.")
+        return rms_avg, rms_on, rms_off
 
     @torch.no_grad()
     def exit_pupil(self, shrink_pupil=False):

@@ -1,6 +1,11 @@
 """Host-side mirror of the reference's `PSFNet` (deeplens/psfnet.py): the PSF-bank workload generators
-(`get_training_data`, `get_test_data`), the MLP prediction `pred`, and the spatially varying dual-pixel `render`.
-Ray tracing and rendering run on libsdirt_engine; the MLP is plain torch (cuBLAS)."""
+(`get_training_data`, `get_test_data`), the fitting loop, the MLP prediction `pred`, and the spatially varying dual-pixel
+`render`.  Ray tracing and rendering run on libsdirt_engine; inside `render` the MLP is the engine's fused tensor-core kernel
+(sdirt_mlp_fused_pred: one launch per band of pixels) with the library-GEMM chain as the route for shapes that kernel is not
+compiled for; `pred` on its own and the fitting step are plain torch."""
+import logging
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -99,6 +104,7 @@ class PSFNet(Lensgroup):
         scaler = torch.amp.GradScaler("cuda")
         ks = self.kernel_size
         losses = []
+        self.eval_history = []
         g = None
         if use_graph:
             static_inp = torch.zeros((bs, 3), device=self.device)
@@ -135,7 +141,23 @@ class PSFNet(Lensgroup):
             scaler.update()
             sche.step()
             if (i + 1) % evaluate_every == 0:
+                # psfnet.py:135-166 without the PNG: checkpoint, then L1 / L2 of the sum-normalised prediction on get_test_data
+                # (1024 grid points x 65536 rays, traced by the engine), logged in the reference's format
+                os.makedirs(result_dir, exist_ok=True)
                 torch.save(psfnet.state_dict(), f"{result_dir}/iter{i + 1}_PSFNet_{self.model_name}.pkl")
+                with torch.no_grad(), torch.autocast(device_type="cuda"):
+                    psfnet.eval()
+                    tin, tpsf = self.get_test_data()
+                    tin, tpsf = tin.to(self.device), tpsf.to(self.device)
+                    tpred = psfnet(tin)
+                    tpsf = tpsf / tpsf.sum(-1).sum(-1).unsqueeze(-1).unsqueeze(-1)
+                    tpred = tpred / tpred.sum(-1).sum(-1).unsqueeze(-1).unsqueeze(-1)
+                    l1_loss, l2_loss = nn.L1Loss(reduction="mean")(tpred, tpsf), l2(tpred, tpsf)
+                    logging.info(f"{i}, {l1_loss.item()}, {l2_loss.item()}")
+                    self.eval_history.append((i, l1_loss.item(), l2_loss.item()))
+                    psfnet.train()
+        os.makedirs(result_dir, exist_ok=True)
+        torch.save(psfnet.state_dict(), f"{result_dir}/PSFNet_{self.model_name}.pkl")          # psfnet.py:167: what the configs load
         return torch.stack(losses).float().cpu().tolist()
 
     # ---- prediction and rendering (psfnet.py:317-336, 589-726) --------------------------------------
@@ -219,7 +241,13 @@ class PSFNet(Lensgroup):
         key = tuple((m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(), m.bias._version) for m in lin)
         cache = getattr(self, "_mlp_fused_cache", None)
         if cache is None or cache[0] != key:
-            cache = self._mlp_fused_cache = (key, E.FusedMlp([(m.weight, m.bias) for m in lin]))
+            # The fused kernel is compiled for kernel sizes 7 / 11 / 21 and layer widths that tile its MMA shape; any other
+            # PSFNet (ks = 9, 31, 35, 51 ...) takes the library-GEMM route (generic pack + generic render kernels): None here.
+            try:
+                packed = E.FusedMlp([(m.weight, m.bias) for m in lin]) if self.kernel_size in (7, 11, 21) else None
+            except RuntimeError:
+                packed = None
+            cache = self._mlp_fused_cache = (key, packed)
         return cache[1]
 
     def _render_post_stream(self, device):
@@ -267,7 +295,8 @@ class PSFNet(Lensgroup):
         if tone & 1:                                                       # degamma once per call, not per band and tile halo
             img32, tone = E.tone_degamma(img32, out=img32 if img32.data_ptr() != img.data_ptr() else None), tone & ~1
         rl, rr = torch.empty_like(img32), torch.empty_like(img32)
-        if self.mlp_engine == "fused":
+        use_fused = self.mlp_engine == "fused" and self._mlp_fused() is not None
+        if use_fused:
             rows, nb = self._fused_band_shape(N, H, W)
         else:
             rows = max(1, min(int(self.render_band_rows), H))
@@ -278,7 +307,7 @@ class PSFNet(Lensgroup):
         post = self._render_post_stream(img.device) if self.render_overlap else main
         n_out = chain[-1][0].shape[1]
         max_px = nb * rows * W
-        fused = self._mlp_fused() if (self.mlp_engine == "fused" and max_px % 4 == 0 and (rows * W) % 4 == 0) else None
+        fused = self._mlp_fused() if (use_fused and max_px % 4 == 0 and (rows * W) % 4 == 0) else None
         raw = [torch.empty((2 * max_px, n_out), device=img.device, dtype=torch.float16) for _ in range(2)] if fused is None else None
         psf = [torch.empty((max_px, 2, ks, ks), device=img.device, dtype=torch.float16) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
@@ -326,10 +355,12 @@ class PSFNet(Lensgroup):
         map [N, 1, H, W] in negative millimetres (psfnet.py:645-714).
 
         The reference builds the per-pixel PSF tensor [N,H,W,2,ks,ks] of the whole batch (`pred`) and then convolves.
-        Here the image is walked in bands of rows: coordinate grid + first Linear (engine kernel), the 512-wide GEMM chain
-        (cuBLAS, bias + ReLU in the GEMM epilogue), flip / stack / normalise (engine kernel), degamma + gather-convolution +
-        gamma + clip (engine kernel) -- the PSFs of a band stay in the L2 between their producer and their consumer, and
-        memory use does not grow with the image."""
+        Here the image is walked in bands of rows.  `mlp_engine = "fused"` (default): ONE tcgen05 kernel per band takes the
+        coordinates through all eleven layers to the flipped / stacked / normalised fp16 kernels (sdirt_mlp_fused_pred), and one
+        kernel convolves them (degamma + gather-convolution + gamma + clip).  `mlp_engine = "cublas"`, and any PSFNet the fused
+        kernel is not compiled for: first Linear (engine kernel), the 512-wide GEMM chain (cuBLAS, bias + ReLU in the epilogue),
+        flip / stack / normalise (engine kernel), then the same convolution -- bit-identical kernels either way.  The PSFs of a
+        band stay in the L2 between their producer and their consumer, and memory use does not grow with the image."""
         render = self._render_banded(img, depth, 1 if train else 3)
         if train:                                                          # noise sits between gamma and clip (:708-713)
             # one draw per call, in the reference's order: noise_range, randn_like, range1, range2 (psfnet.py:629-642)
@@ -381,6 +412,27 @@ class PSFNet(Lensgroup):
             render = self.noise(render, img.shape)
             render = torch.clip(render, 0.0, 1.0)
         return render
+
+    @torch.no_grad()
+    def compare_psf(self):
+        """The data of PSFNet.compare_psf (psfnet.py:529-566) without its PNGs: for the three field points (0, 0), (0.4, 0.4),
+        (0.8, 0.8) at 0.5 m and 20 m, the ray-traced (left, right) PSFs -- the right one from the mirrored point, flipped, as the
+        reference obtains it -- and the network's prediction.  Returns {distance: (traced [3, 2, ks, ks], predicted [3, 2, ks, ks])}."""
+        from .basics import GEO_SPP
+        x = torch.Tensor([0, 0.4, 0.8])
+        y = torch.Tensor([0, 0.4, 0.8])
+        out = {}
+        for d_ori in (-500.0, -20000.0):
+            depth = d_ori + self.d_sensor
+            inp = torch.stack((x, y, torch.full_like(x, depth)), dim=-1)
+            psfl = self.psf(points=inp, ks=self.kernel_size, center=True, spp=GEO_SPP * 100).cpu()
+            inp[..., 0] = inp[..., 0] * (-1)
+            psfr = torch.flip(self.psf(points=inp, ks=self.kernel_size, center=True, spp=GEO_SPP * 100).cpu(), dims=[-1])
+            z = float(self.depth2z(torch.tensor(depth)))
+            net_in = torch.stack((x, y, torch.full_like(x, z)), dim=-1).repeat(1, 1, 1, 1).to(self.device)
+            pred = self.pred(net_in).detach().float().cpu()[0, 0]                                   # [3, 2, ks, ks]
+            out[int(d_ori)] = (torch.stack((psfl, psfr), dim=1), pred)
+        return out
 
     def depth2z(self, depth):
         return torch.clamp((depth - self.d_min) / (self.d_max - self.d_min), min=0, max=1)

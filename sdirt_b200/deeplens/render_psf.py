@@ -26,12 +26,19 @@ def local_psf_render_fast(input, psf, kernel_size=11, val=False):
 
 
 def local_psf_render(input, psf, kernel_size=11, val=False):
-    """Same arithmetic, other layout (render_psf.py:76-118)."""
+    """(rl, rr) like local_psf_render_fast: the reference's older formulation of the same half() arithmetic (render_psf.py:76-118;
+    its docstring still describes a single-PSF signature, its body reshapes `psf` to [-1, 2, ks, ks] and returns the pair)."""
     return local_psf_render_fast(input, psf, kernel_size, val)
 
 
 def local_dp_psf_render(input, dp_psf, kernel_size=21):
-    """[N, 2C, H, W] = cat(left, right) (render_psf.py:157-188).  NOTE: the reference runs this variant in the
-    input dtype; the engine always follows the fp16 path of local_psf_render_fast."""
-    rl, rr = local_psf_render_fast(input, dp_psf, kernel_size)
+    """[N, 2C, H, W] = cat(left, right) (render_psf.py:157-188).  The reference does NOT cast this variant to half: the
+    arithmetic runs in the promoted dtype of `input` and `dp_psf` -- float32 unless both are half."""
+    if input.dtype == torch.float16 and dp_psf.dtype == torch.float16:
+        rl, rr = local_psf_render_fast(input, dp_psf, kernel_size)
+        return torch.cat([rl, rr], dim=1)
+    b, c, h, w = input.shape
+    img = input.float().contiguous()
+    psf = dp_psf.float().reshape(b, h, w, 2, kernel_size, kernel_size).contiguous()
+    rl, rr = E.render_local_psf_f32(img, psf, kernel_size)
     return torch.cat([rl, rr], dim=1)

@@ -244,7 +244,85 @@ def golden_psf2m_sweep():
     torch.manual_seed(21)
     torch.rand(spp), torch.rand(spp)
     out["centre"] = lens.psf_center(obj).numpy()
+    # the bundle-global Newton loop counts of the two five-point bundles psf_diff traced (surfaces.py:543-561 `while any()`):
+    # what sdirt_psf_bank replays in the `replay` parity test
+    counts = []
+    for i in range(0, len(pts), 5):
+        torch.manual_seed(21)
+        ray = lens.sample_from_points(o=obj[i:i + 5], spp=spp)
+        counts.append(newton_counts(lens, ray)[2])
+    out["newton_counts"] = np.asarray(counts, np.int32)
     np.savez_compressed(os.path.join(HERE, "psf2m_sweep.npz"), **out)
+
+
+def golden_rf35mm2m():
+    """BASELINE config 3's prescription at the config-2 sample count: 2 M rays per point through the 21 surfaces of rf35mm,
+    on axis at 2 m, the field corner at 20 m (coarsest first-hit lattice) and mid field at 0.7 m; with the bundle-global
+    Newton loop counts for the replay test."""
+    out = {}
+    spp = 2_000_000
+    lens = make_lens("rf35mm")
+    ds = lens.d_sensor
+    pts = torch.tensor([[0, 0, -2000 + ds], [0.98, -0.98, -20000 + ds], [0.4, 0.3, -700 + ds]], dtype=torch.float32)
+    out["points_norm"] = pts.numpy()
+    out["hfov"] = np.float64(lens.hfov)
+    pz, pr = lens.entrance_pupil()
+    out["pupil"] = np.asarray([pz, pr], np.float64)
+    for tag in ("l", "r"):
+        torch.manual_seed(33)
+        u = [torch.rand(spp).numpy() for _ in range(2)]
+        torch.manual_seed(33)
+        out[tag] = lens.psf_diff(pts, ks=21, spp=spp, param_list=DP + (tag,)).numpy()
+        out["u_check"] = np.asarray([float(v.astype(np.float64).sum()) for v in u] + [spp])
+    scale = lens.calc_scale_pinhole(pts[:, 2])
+    obj = pts.clone()
+    obj[:, 0] = pts[:, 0] * scale * lens.sensor_size[1] / 2
+    obj[:, 1] = pts[:, 1] * scale * lens.sensor_size[0] / 2
+    out["points_obj"] = obj.numpy()
+    torch.manual_seed(33)
+    torch.rand(spp), torch.rand(spp)
+    out["centre"] = lens.psf_center(obj).numpy()
+    torch.manual_seed(33)
+    ray = lens.sample_from_points(o=obj, spp=spp)
+    out["newton_counts"] = np.asarray(newton_counts(lens, ray)[2], np.int32)
+    np.savez_compressed(os.path.join(HERE, "rf35mm2m.npz"), **out)
+
+
+def golden_api():
+    """Seeded outputs of the API entry points around the hot path that round 1 left untested: the two other render
+    variants (render_psf.py:76-118, 157-188), psf_map (optics.py:1018-1041), get_training_data / get_test_data
+    (psfnet.py:170-241), analysis_rms and calc_magnification3 (optics.py:2103-2140, 1237-1272)."""
+    from deeplens.render_psf import local_psf_render, local_dp_psf_render
+    out = {}
+    torch.manual_seed(17)
+    for ks, (b, h, w) in ((7, (2, 12, 20)), (11, (1, 10, 16))):
+        img = torch.rand(b, 3, h, w)
+        psf = torch.rand(b, h, w, 2, ks, ks) ** 4
+        psf = psf / psf.sum((-1, -2), keepdim=True)
+        rl, rr = local_psf_render(img, psf, ks)
+        out[f"rv{ks}_img"], out[f"rv{ks}_psf"] = img.numpy(), psf.numpy()
+        out[f"rv{ks}_rl"], out[f"rv{ks}_rr"] = rl.numpy(), rr.numpy()
+        out[f"rv{ks}_dp"] = local_dp_psf_render(img, psf, ks).numpy()            # float32 arithmetic
+    for name in LENSES:
+        lens = make_lens(name)
+        ds = lens.d_sensor
+        torch.manual_seed(4)
+        out[f"{name}_psf_map"] = lens.psf_map(depth=-1500.0 + ds, grid=3, ks=11, spp=20000).numpy()
+        torch.manual_seed(4)
+        out[f"{name}_psf_map_u"] = np.stack([torch.rand(20000).numpy(), torch.rand(20000).numpy()])
+        np.random.seed(8)
+        torch.manual_seed(8)
+        inp, psf = lens.get_training_data(bs=8, spp=20000)
+        out[f"{name}_train_inp"], out[f"{name}_train_psf"] = inp.numpy(), psf.numpy()
+        torch.manual_seed(9)
+        inp, psf = lens.get_test_data(bs=1024, spp=2048)
+        out[f"{name}_test_inp"], out[f"{name}_test_psf"] = inp.numpy(), psf.numpy()[::16]
+        torch.manual_seed(10)
+        out[f"{name}_mag3"] = np.asarray([lens.calc_magnification3(-1000.0 + ds), lens.calc_magnification3(-20000.0 + ds)], np.float64)
+        torch.manual_seed(11)
+        out[f"{name}_rms"] = np.asarray([float(v) for v in lens.analysis_rms(depth=-1000.0 + ds)] +
+                                        [float(v) for v in lens.analysis_rms(depth=-5000.0 + ds)], np.float64)
+    np.savez_compressed(os.path.join(HERE, "api.npz"), **out)
 
 
 def _psf_same_seed(lens, pts, spp, tag):
@@ -327,7 +405,7 @@ def golden_predhalf():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["setup", "trace", "dp", "psf", "psf2m", "render", "predhalf"]
+    which = sys.argv[1:] or ["setup", "trace", "dp", "psf", "psf2m", "psf2m_sweep", "rf35mm2m", "render", "predhalf", "api"]
     for w in which:
         globals()[f"golden_{w}"]()
         print("wrote", w)
