@@ -552,18 +552,22 @@ render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ ps
             __syncwarp();
             mbar_wait(pfull + pb, (unsigned)(ly / RL_PBUF) & 1u);
             const float *pr = part + pb * (G::NW * RP_C * 32);
+            float v[RP_C];
 #pragma unroll
             for (int c = 0; c < RP_C; ++c) {
                 const float *ps = pr + (s * (G::NW / 2)) * (RP_C * 32) + c * 32 + lane;
-                float v = 0.0f;
+                v[c] = 0.0f;
 #pragma unroll
-                for (int k = 0; k < G::NW / 2; ++k) v += ps[k * (RP_C * 32)];
-                v = __half2float(__float2half_rn(v));
-                if (tone & 2) v = fminf(fmaxf(tone_gamma(v), 0.0f), 1.0f);
-                (s ? out_r : out_l)[(((int64_t)b * RP_C + c) * H + (y0 + ly)) * W + (x0 + lane)] = v;
+                for (int k = 0; k < G::NW / 2; ++k) v[c] += ps[k * (RP_C * 32)];
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(pempty + pb);
+            if (lane == 0) mbar_arrive(pempty + pb);           // the partial sums are in registers: the buffer goes back before the tone curve
+#pragma unroll
+            for (int c = 0; c < RP_C; ++c) {
+                float o = __half2float(__float2half_rn(v[c]));
+                if (tone & 2) o = fminf(fmaxf(tone_gamma(o), 0.0f), 1.0f);
+                (s ? out_r : out_l)[(((int64_t)b * RP_C + c) * H + (y0 + ly)) * W + (x0 + lane)] = o;
+            }
         }
         return;
     }

@@ -10,7 +10,7 @@ import torch
 
 from conftest import lens_path
 from oracle import dp_oracle as O
-from test_oracle_golden import D_SENSOR, arbiter_in_focus_corner, l1_sumnorm, make_lens, psf_golden_samples, torch_pupil
+from test_oracle_golden import D_SENSOR, arbiter_in_focus_corner, arbiter_psf, l1_sumnorm, make_lens, psf_golden_samples, torch_pupil
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -989,4 +989,16 @@ def test_rf35mm_psf_bank_2m_rays(golden, numerics):
     l1l, l1r = l1_sumnorm(L.cpu().numpy(), g["l"]), l1_sumnorm(R.cpu().numpy(), g["r"])
     print("rf35mm", numerics, "2M-ray L1 (L):", l1l, "(R):", l1r)
     tol = {"replay": 2e-5, "fast": 1.5e-4}.get(numerics, 1e-4)
-    assert l1l.max() < tol and l1r.max() < tol
+    # Point 1 (field corner at 20 m) is nearly in focus for this lens: eight taps carry the PSF, and the reference's sequential
+    # float32 `index_put_` sums are 3.4e-4 (L) / 1.2e-4 (R) from the exact sum of their own addends
+    # (test_rf35mm_far_corner_reference_vs_float64_sum).  There the engine is held to the arbiter -- the reference's rays and
+    # addends summed in float64 -- and must be the closer side; everywhere else to the reference itself.
+    others = [0, 2]
+    assert l1l[others].max() < tol and l1r[others].max() < tol
+    L64, R64 = arbiter_psf(g, "rf35mm", 1, 33, g["newton_counts"])
+    d_l = l1_sumnorm(L[1:2].cpu().numpy().astype(np.float64), L64[None])[0]
+    d_r = l1_sumnorm(R[1:2].cpu().numpy().astype(np.float64), R64[None])[0]
+    ref_l = l1_sumnorm(g["l"][1:2].astype(np.float64), L64[None])[0]
+    ref_r = l1_sumnorm(g["r"][1:2].astype(np.float64), R64[None])[0]
+    print(f"rf35mm {numerics} 20 m corner vs float64 sum: {d_l:.2e} / {d_r:.2e}; reference vs float64 sum: {ref_l:.2e} / {ref_r:.2e}")
+    assert max(d_l, d_r) < tol and d_l < ref_l and d_r < ref_r
