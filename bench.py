@@ -372,7 +372,7 @@ def run_gpu(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    e2e_steps = max(2, min(args.steps, 4))
+    e2e_steps = max(2, min(args.steps, 8))              # (the same slabs as the timed steps of `value`, when K <= 8)
     # the shared sample set of the end-to-end calls is drawn on the device (the reference draws it on the host and uploads it,
     # optics.py:483-487: that serial host work is identical on every rank and cost the 8-GPU end-to-end number 6 % in round 1);
     # the object points still come from host memory and the PSFs still go back to it, every step
@@ -429,14 +429,14 @@ def run_gpu(args):
         # leave the rank with the far half 15 % behind); world sizes that do not divide 32 fall back to contiguous point blocks
         strided = DEPTHS % world == 0
         if strided:
-            my_slabs = list(range(rank, DEPTHS, world))
+            my_slabs = sharding.dealt_groups(DEPTHS, rank, world)
             allpts = torch.cat([lens._object_points(bank_points(s, lens=LENS)) for s in my_slabs], 0).to(dev).contiguous()
         else:
             sl = sharding.shard_slice(P, rank, world)
             allpts = torch.cat([lens._object_points(bank_points(s, lens=LENS)) for s in range(DEPTHS)], 0)[sl].to(dev).contiguous()
         cp = (pupil[:2048] * 0.25).contiguous()
         local_out = torch.empty((allpts.shape[0], 2, KS, KS), dtype=torch.float32, device=dev)
-        gathered = torch.empty((P, 2, KS, KS), dtype=torch.float32, device=dev) if world > 1 else None
+        gathered = torch.empty((P, 2, KS, KS), dtype=torch.float32, device=dev) if (world > 1 and strided) else None
         bank = torch.empty((P, 2, KS, KS), dtype=torch.float32, device=dev) if (world > 1 and strided) else None
 
         def full_bank():
@@ -450,14 +450,9 @@ def run_gpu(args):
             """The ONE collective of the path (north_star): every rank ends up with the whole 462 MB bank, in depth-major order."""
             if world == 1:
                 return local_out
-            if sharding.shard_bounds(P, world)[1] * world != P:
-                return sharding.gather_blocks(local_out, P)
-            dist.all_gather_into_tensor(gathered, local_out)
             if not strided:
-                return gathered
-            # [rank][local slab] -> [slab = local * N + rank]
-            bank.view(DEPTHS // world, world, block, 2, KS, KS).copy_(gathered.view(world, DEPTHS // world, block, 2, KS, KS).transpose(0, 1))
-            return bank
+                return sharding.gather_blocks(local_out, P)
+            return sharding.gather_dealt(local_out, DEPTHS, out=bank, scratch=gathered)
 
         full_bank()                                                    # warm
         assemble()

@@ -42,6 +42,38 @@ def gather_blocks(local, n_total, group=None):
     return torch.cat([out[r, : bounds[r + 1] - bounds[r]] for r in range(world)], dim=0)
 
 
+def dealt_groups(n_groups, rank=None, world_size=None):
+    """Round-robin dealing of equal-sized groups (the depth slabs of a PSF bank): rank r owns groups r, r + G, r + 2G, ...
+    Near and far slabs cost differently (far object points take the strict first surface), so contiguous blocks of depths leave
+    the rank with the far end behind; dealing gives every rank the same mix.  Requires n_groups % world_size == 0."""
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if n_groups % world_size:
+        raise ValueError(f"{n_groups} groups cannot be dealt evenly to {world_size} ranks")
+    return list(range(rank, n_groups, world_size))
+
+
+def gather_dealt(local, n_groups, out=None, scratch=None, group=None):
+    """Assemble groups dealt by `dealt_groups` on every rank, in group order: ONE all_gather_into_tensor of the per-rank
+    blocks [n_groups / G * g, ...] (g = rows per group) and one device-side reorder [rank][local group] -> [group].
+    `out` / `scratch` (both [n_groups * g, ...]) may be passed in to keep the call allocation-free."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    per = n_groups // world
+    g = local.shape[0] // per
+    tail = tuple(local.shape[1:])
+    if scratch is None:
+        scratch = torch.empty((n_groups * g,) + tail, dtype=local.dtype, device=local.device)
+    if out is None:
+        out = torch.empty_like(scratch)
+    dist.all_gather_into_tensor(scratch, local.contiguous(), group=group)
+    out.view((per, world, g) + tail).copy_(scratch.view((world, per, g) + tail).transpose(0, 1))
+    return out
+
+
 def psf_bank_sharded(lens, points, ks, spp, wvln=0.589, param_list=None, gather=True, seed=None, group=None):
     """DP PSF bank for normalised points [P, 3], sharded by points.  Returns (L, R): the full [P, ks, ks] bank on
     every rank if `gather`, else this rank's block.  All ranks draw the SAME pupil samples (same CPU seed), as the

@@ -150,7 +150,7 @@ def test_fit_script_sequence(tmp_path, monkeypatch, capsys):
         for traced, pred in cmp.values():
             assert traced.shape == pred.shape == (3, 2, ks, ks) and torch.isfinite(traced).all() and torch.isfinite(pred).all()
             # on axis the right PSF is the mirror image of the left one (different samples: to sampling noise)
-            assert l1_sumnorm(traced[0:1, 0].numpy(), torch.flip(traced[0:1, 1], dims=[-1]).numpy())[0] < 0.02
+            assert l1_sumnorm(traced[0:1, 0].numpy(), torch.flip(traced[0:1, 1], dims=[-1]).numpy())[0] < 0.05
     finally:
         for h in list(logging.getLogger().handlers):
             if h not in handlers:

@@ -120,6 +120,33 @@ def test_gather_blocks_gloo_world2():
     assert all(ret[r] for r in range(world))
 
 
+def _dealt_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from sdirt_b200.sharding import dealt_groups, gather_dealt
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_groups, g = 8, 3
+    full = torch.arange(n_groups * g * 2 * 4, dtype=torch.float32).reshape(n_groups * g, 2, 4)
+    mine = dealt_groups(n_groups)
+    local = torch.cat([full[k * g:(k + 1) * g] for k in mine])
+    out = gather_dealt(local, n_groups)
+    ret[rank] = bool(torch.equal(out, full)) and mine == list(range(rank, n_groups, world))
+    dist.destroy_process_group()
+
+
+def test_gather_dealt_gloo_world2():
+    """The strong-scaling assembly of bench.py's `strong` leg: depth slabs dealt round-robin, one all-gather, reorder."""
+    world, port = 2, 31500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dealt_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
+    from sdirt_b200.sharding import dealt_groups
+    assert dealt_groups(32, 3, 8) == [3, 11, 19, 27]
+    with pytest.raises(ValueError):
+        dealt_groups(32, 0, 3)
+
+
 def test_bench_workload_shape():
     sys.path.insert(0, ROOT)
     import bench
