@@ -308,7 +308,7 @@ class Lensgroup(DeepObj):
         self._require_cuda()
         if not torch.is_tensor(points):
             points = torch.tensor(points)
-        points = points.float().cpu()
+        points = points.float() if points.is_cuda else points.float().cpu()      # (device points stay there: no host round trip)
         if points.dim() == 1:
             points = points.unsqueeze(0)
         point_obj = self._object_points(points)

@@ -86,6 +86,25 @@ class PSFNet(Lensgroup):
         return inp, self.psf(points=points, ks=self.kernel_size, spp=spp)
 
     fit_graph = True                 # capture forward + loss + backward of the fitting step in a CUDA graph
+    fit_device_data = False          # train_psfnet: draw the batch's (x, y, z) and the shared pupil samples on the DEVICE and keep
+                                     # the evaluation bank (get_test_data) resident between evaluations -- no host RNG, no
+                                     # per-iteration upload.  Off by default: a seeded run then draws what the reference draws.
+
+    def _training_data_device(self, bs, spp):
+        """get_training_data with every draw on the device generator (same distributions, psfnet.py:170-199)."""
+        foc_z = float(np.random.choice(self.foc_z_arr))
+        x = (torch.rand(bs, device=self.device) - 0.5) * 2
+        y = (torch.rand(bs, device=self.device) - 0.5) * 2
+        zg = torch.clamp(torch.randn(bs, device=self.device), min=-3, max=3)
+        z = torch.where(zg > 0, (1 - foc_z) * zg / 3 + foc_z, torch.where(zg < 0, foc_z * zg / 3 + foc_z, torch.zeros_like(zg)))
+        inp = torch.stack((x, y, z), dim=-1)
+        points = torch.stack((x, y, self.z2depth(z)), dim=-1)
+        prev = getattr(self, "sample_rng", "cpu")
+        self.sample_rng = "cuda"
+        try:
+            return inp, self.psf(points=points, ks=self.kernel_size, spp=spp)
+        finally:
+            self.sample_rng = prev
 
     def train_psfnet(self, iters=10000, bs=128, lr=1e-4, spp=2048, evaluate_every=1000, result_dir="./results/temp", graph=None):
         """Fit the PSF MLP to ray-traced PSFs generated on the fly (psfnet.py:101-167); no plotting.
@@ -124,7 +143,7 @@ class PSFNet(Lensgroup):
                     static_loss = l2(psfnet(static_inp), static_psf)
                 scaler.scale(static_loss).backward()
         for i in range(iters + 1):
-            inp, psf = self.get_training_data(bs=bs, spp=spp)
+            inp, psf = self._training_data_device(bs, spp) if self.fit_device_data else self.get_training_data(bs=bs, spp=spp)
             inp, psf = inp.to(self.device), psf.to(self.device)
             if g is not None:
                 static_inp.copy_(inp)
@@ -147,8 +166,13 @@ class PSFNet(Lensgroup):
                 torch.save(psfnet.state_dict(), f"{result_dir}/iter{i + 1}_PSFNet_{self.model_name}.pkl")
                 with torch.no_grad(), torch.autocast(device_type="cuda"):
                     psfnet.eval()
-                    tin, tpsf = self.get_test_data()
-                    tin, tpsf = tin.to(self.device), tpsf.to(self.device)
+                    if self.fit_device_data and getattr(self, "_test_bank", None) is not None and self._test_bank[0] == float(self.d_sensor):
+                        tin, tpsf = self._test_bank[1], self._test_bank[2]          # the evaluation bank, traced once
+                    else:
+                        tin, tpsf = self.get_test_data()
+                        tin, tpsf = tin.to(self.device), tpsf.to(self.device)
+                        if self.fit_device_data:
+                            self._test_bank = (float(self.d_sensor), tin, tpsf)
                     tpred = psfnet(tin)
                     tpsf = tpsf / tpsf.sum(-1).sum(-1).unsqueeze(-1).unsqueeze(-1)
                     tpred = tpred / tpred.sum(-1).sum(-1).unsqueeze(-1).unsqueeze(-1)

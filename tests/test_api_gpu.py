@@ -201,6 +201,15 @@ def test_psfnet_fitting_loop(tmp_path, lenses):
         fresh.numerics = "adaptive"
         runs.append(fresh.train_psfnet(iters=5, bs=16, spp=2000, evaluate_every=10 ** 9, result_dir=str(tmp_path), graph=use_graph))
     np.testing.assert_allclose(runs[0], runs[1], rtol=2e-2)
+    # everything on the device: batch coordinates and pupil samples from the CUDA generator, the evaluation bank traced once
+    fresh.fit_device_data = True
+    torch.cuda.manual_seed(3)
+    hist = fresh.train_psfnet(iters=5, bs=16, spp=2000, evaluate_every=3, result_dir=str(tmp_path))
+    assert len(hist) == 6 and all(np.isfinite(hist)) and len(fresh.eval_history) == 2
+    bank = fresh._test_bank
+    assert bank[1].is_cuda and bank[2].shape == (1024, 21, 21) and float(bank[2].amax((1, 2)).min()) > 0.99
+    a, b = fresh._training_data_device(64, 4000)
+    assert a.is_cuda and b.is_cuda and float(a[:, 2].min()) >= 0 and float(a[:, 2].max()) <= 1 and float(b.amax((1, 2)).min()) > 0.99
 
 
 def test_render_banded_vs_reference_half(golden):
