@@ -472,6 +472,11 @@ __device__ __forceinline__ void lane_row(const unsigned char *kb, const unsigned
 // Warp roles: warps 0 .. NW-1 compute (each a few kernel rows of one side, lanes = the 32 pixels of the row segment);
 // warps NW, NW+1 reduce one side each (add its NW/2 partial sums, round, tone-map, write the pixels); lane 0 of the first
 // also issues the bulk copies.  Everything between the roles is an mbarrier: compute warps never meet a CTA-wide barrier in the row loop.
+// Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (x, y, image) grid and the ring of
+// kernel stages runs THROUGH the tile boundaries -- the streamer keeps a cursor (tile, row) of the next row to fetch and fills a
+// stage as soon as the compute warps let go of it, whether that row belongs to this tile or the next.  With one 16-row tile per
+// CTA the ring was filled and drained once per tile with nothing else resident on the SM to cover it (0.79 of the HBM roofline);
+// now the only reload between tiles is the 35 KB image tile, taken while three rows of the next tile are already in flight.
 template <int KS>
 __global__ void __launch_bounds__((LaneGeom<KS>::NW + 2) * 32, 1)
 render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ psf, int B, int H, int W, int row0, int nrw, int tone,
@@ -484,9 +489,18 @@ render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ ps
     unsigned long long *full = reinterpret_cast<unsigned long long *>(rl_raw + G::BAR_OFF), *empty = full + RS_STAGES;
     unsigned long long *pfull = empty + RS_STAGES, *pempty = pfull + RL_PBUF;
     constexpr int pad = (KS - 1) / 2, SEG = G::SEG, CHB = 4 * G::CHW;
-    const int b = blockIdx.z, y0 = row0 + blockIdx.y * RP_TH, x0 = blockIdx.x * SEG;
-    const int nrows = min(RP_TH, row0 + nrw - y0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx_n = W / SEG, ty_n = (nrw + RP_TH - 1) / RP_TH;
+    const int n_tiles = tx_n * ty_n * B;
+    // tile t -> image b, first row y0, first column x0, rows in the tile
+    auto decode = [&](int t, int &b, int &y0, int &x0, int &nrows) {
+        const int tx = t % tx_n, r = t / tx_n;
+        const int ty = r % ty_n;
+        b = r / ty_n;
+        y0 = row0 + ty * RP_TH;
+        x0 = tx * SEG;
+        nrows = min(RP_TH, row0 + nrw - y0);
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < RS_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, G::NW); }
@@ -494,85 +508,21 @@ render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ ps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int row) {
-        const int st = row % RS_STAGES;
+    // the streamer's cursor (lane 0 of the first reducer warp): next row to fetch = row p_row of tile p_t, ring position p_g
+    int p_t = blockIdx.x, p_row = 0, p_g = 0;
+    auto issue_next = [&]() {
+        int b, y0, x0, nrows;
+        decode(p_t, b, y0, x0, nrows);
+        const int st = p_g % RS_STAGES;
         mbar_expect_tx(full + st, G::STAGE_BYTES);
-        bulk_g2s(rl_raw + st * G::STAGE_BYTES, psf + (((int64_t)b * nrw + (y0 - row0 + row)) * W + x0) * (2 * KS * KS), G::STAGE_BYTES, full + st);
+        bulk_g2s(rl_raw + st * G::STAGE_BYTES, psf + (((int64_t)b * nrw + (y0 - row0 + p_row)) * W + x0) * (2 * KS * KS), G::STAGE_BYTES, full + st);
+        ++p_g;
+        if (++p_row == nrows) { p_row = 0; p_t += gridDim.x; }
     };
     if (warp == G::NW && lane == 0)
-        for (int row = 0; row < min(RS_STAGES, nrows); ++row) issue(row);
+        for (int k = 0; k < RS_STAGES && p_t < n_tiles; ++k) issue_next();
 
-    // ---- image tile, column-mirrored: copy 0 (elements 2w, 2w+1 per word) and two instances of copy 1 (2w+1, 2w+2) ----
-    // loads first, eight at a time, so that a thread waits for HBM once per batch and not once per element
-    constexpr int TILE_ELEMS = RP_C * G::TH * 2 * G::RW;
-    for (int i0 = threadIdx.x; i0 < TILE_ELEMS; i0 += 8 * blockDim.x) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int i = i0 + k * blockDim.x;
-            v[k] = 0.0f;
-            if (i < TILE_ELEMS) {
-                const int c = i / (G::TH * 2 * G::RW), rem = i - c * (G::TH * 2 * G::RW);
-                const int r = rem / (2 * G::RW), m = rem - r * (2 * G::RW);
-                if (m < G::TW) {
-                    const int gy = min(max(y0 + r - pad, 0), H - 1), gx = min(max(x0 + (G::TW - 1 - m) - pad, 0), W - 1);
-                    v[k] = __ldg(img + (((int64_t)b * RP_C + c) * H + gy) * W + gx);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int i = i0 + k * blockDim.x;
-            if (i < TILE_ELEMS) {
-                const int m = i % (2 * G::RW);
-                s0h[i] = __float2half_rn((tone & 1) && m < G::TW ? tone_degamma(v[k]) : v[k]);
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < G::COPY_RAW; i += blockDim.x) {
-        const int w = i % G::RW;
-        const __half lo = s0h[2 * i + 1];
-        const __half hi = (w + 1 < G::RW) ? s0h[2 * i + 2] : __float2half_rn(0.0f);
-        const unsigned word = (unsigned)__half_as_ushort(lo) | ((unsigned)__half_as_ushort(hi) << 16);
-        tile[G::COPY1A + i] = word;
-        tile[G::COPY1B + i] = word;
-    }
-    __syncthreads();
-
-    if (warp >= G::NW) {
-        // ---- reducer warps (one per side; the first also streams) ------------------------------------------------------------
-        const int s = warp - G::NW;
-        for (int ly = 0; ly < nrows; ++ly) {
-            const int st = ly % RS_STAGES, pb = ly % RL_PBUF;
-            if (s == 0 && lane == 0 && ly + RS_STAGES < nrows) {  // the stage of row ly is free once every compute warp let go
-                mbar_wait(empty + st, (unsigned)(ly / RS_STAGES) & 1u);
-                issue(ly + RS_STAGES);
-            }
-            __syncwarp();
-            mbar_wait(pfull + pb, (unsigned)(ly / RL_PBUF) & 1u);
-            const float *pr = part + pb * (G::NW * RP_C * 32);
-            float v[RP_C];
-#pragma unroll
-            for (int c = 0; c < RP_C; ++c) {
-                const float *ps = pr + (s * (G::NW / 2)) * (RP_C * 32) + c * 32 + lane;
-                v[c] = 0.0f;
-#pragma unroll
-                for (int k = 0; k < G::NW / 2; ++k) v[c] += ps[k * (RP_C * 32)];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pempty + pb);           // the partial sums are in registers: the buffer goes back before the tone curve
-#pragma unroll
-            for (int c = 0; c < RP_C; ++c) {
-                float o = __half2float(__float2half_rn(v[c]));
-                if (tone & 2) o = fminf(fmaxf(tone_gamma(o), 0.0f), 1.0f);
-                (s ? out_r : out_l)[(((int64_t)b * RP_C + c) * H + (y0 + ly)) * W + (x0 + lane)] = o;
-            }
-        }
-        return;
-    }
-
-    // ---- compute warps: this warp's kernel rows and this lane's pixel ---------------------------------------------------------
+    // compute warps: this warp's kernel rows and this lane's pixel (constant over the tiles)
     // pixel lx = lane; tap (u, v) multiplies mirrored tile element (row ly + KS-1-u, m = SEG-1-lane + v)
     const int side = warp / (G::NW / 2), u0 = (warp - side * (G::NW / 2)) * G::TPW;
     const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
@@ -582,27 +532,105 @@ render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ ps
     const int img1 = (lane & 1) ? 4 * (G::COPY1B + ((SEG - 1 - lane) >> 1)) : 4 * ((SEG - lane) >> 1);
     const int sgl0 = 2 * (SEG - 1 - lane + KS - 1), sgl1 = 2 * (SEG - 1 - lane);      // single taps: v = KS-1 (P0 = 0), v = 0 (P0 = 1)
 
-    for (int ly = 0; ly < nrows; ++ly) {
-        const int st = ly % RS_STAGES, pb = ly % RL_PBUF;
-        mbar_wait(full + st, (unsigned)(ly / RS_STAGES) & 1u);
-        const unsigned char *kblock = rl_raw + st * G::STAGE_BYTES + lane * G::PIX_BYTES + 2 * side * KS * KS;
-        float acc[RP_C];
+    int g0 = 0;                                             // rows this CTA has been through before the current tile (ring position)
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int b, y0, x0, nrows;
+        decode(t, b, y0, x0, nrows);
+
+        // ---- image tile, column-mirrored: copy 0 (elements 2w, 2w+1 per word) and two instances of copy 1 (2w+1, 2w+2) ----
+        // loads first, eight at a time, so that a thread waits for HBM once per batch and not once per element
+        constexpr int TILE_ELEMS = RP_C * G::TH * 2 * G::RW;
+        for (int i0 = threadIdx.x; i0 < TILE_ELEMS; i0 += 8 * blockDim.x) {
+            float v[8];
 #pragma unroll
-        for (int c = 0; c < RP_C; ++c) acc[c] = 0.0f;
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + k * blockDim.x;
+                v[k] = 0.0f;
+                if (i < TILE_ELEMS) {
+                    const int c = i / (G::TH * 2 * G::RW), rem = i - c * (G::TH * 2 * G::RW);
+                    const int r = rem / (2 * G::RW), m = rem - r * (2 * G::RW);
+                    if (m < G::TW) {
+                        const int gy = min(max(y0 + r - pad, 0), H - 1), gx = min(max(x0 + (G::TW - 1 - m) - pad, 0), W - 1);
+                        v[k] = __ldg(img + (((int64_t)b * RP_C + c) * H + gy) * W + gx);
+                    }
+                }
+            }
 #pragma unroll
-        for (int t = 0; t < G::TPW; ++t) {
-            const int u = u0 + t;
-            const unsigned char *kb = kblock + 2 * u * KS;
-            const unsigned char *rowb = tb + 4 * ((ly + KS - 1 - u) * G::RW);
-            if ((side + u) & 1) lane_row<KS, 1, CHB>(kb, rowb + img1, rowb + sgl1, acc);
-            else lane_row<KS, 0, CHB>(kb, rowb + img0, rowb + sgl0, acc);
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + k * blockDim.x;
+                if (i < TILE_ELEMS) {
+                    const int m = i % (2 * G::RW);
+                    s0h[i] = __float2half_rn((tone & 1) && m < G::TW ? tone_degamma(v[k]) : v[k]);
+                }
+            }
         }
-        if (ly >= RL_PBUF) mbar_wait(pempty + pb, (unsigned)(ly / RL_PBUF - 1) & 1u);   // the reducer is done with this buffer
-        float *pw = part + (pb * G::NW + warp) * (RP_C * 32);
+        __syncthreads();
+        for (int i = threadIdx.x; i < G::COPY_RAW; i += blockDim.x) {
+            const int w = i % G::RW;
+            const __half lo = s0h[2 * i + 1];
+            const __half hi = (w + 1 < G::RW) ? s0h[2 * i + 2] : __float2half_rn(0.0f);
+            const unsigned word = (unsigned)__half_as_ushort(lo) | ((unsigned)__half_as_ushort(hi) << 16);
+            tile[G::COPY1A + i] = word;
+            tile[G::COPY1B + i] = word;
+        }
+        __syncthreads();
+
+        if (warp >= G::NW) {
+            // ---- reducer warps (one per side; the first also streams) --------------------------------------------------------
+            const int s = warp - G::NW;
+            for (int ly = 0; ly < nrows; ++ly) {
+                const int g = g0 + ly, st = g % RS_STAGES, pb = g % RL_PBUF;
+                if (s == 0 && lane == 0 && p_t < n_tiles) {       // the stage of row g is free once every compute warp let go
+                    mbar_wait(empty + st, (unsigned)(g / RS_STAGES) & 1u);
+                    issue_next();                                 // row g + RS_STAGES of the ring: this tile's or the next one's
+                }
+                __syncwarp();
+                mbar_wait(pfull + pb, (unsigned)(g / RL_PBUF) & 1u);
+                const float *pr = part + pb * (G::NW * RP_C * 32);
+                float v[RP_C];
 #pragma unroll
-        for (int c = 0; c < RP_C; ++c) pw[c * 32 + lane] = acc[c];
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(empty + st); mbar_arrive(pfull + pb); }
+                for (int c = 0; c < RP_C; ++c) {
+                    const float *ps = pr + (s * (G::NW / 2)) * (RP_C * 32) + c * 32 + lane;
+                    v[c] = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < G::NW / 2; ++k) v[c] += ps[k * (RP_C * 32)];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pempty + pb);           // the partial sums are in registers: the buffer goes back before the tone curve
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) {
+                    float o = __half2float(__float2half_rn(v[c]));
+                    if (tone & 2) o = fminf(fmaxf(tone_gamma(o), 0.0f), 1.0f);
+                    (s ? out_r : out_l)[(((int64_t)b * RP_C + c) * H + (y0 + ly)) * W + (x0 + lane)] = o;
+                }
+            }
+        } else {
+            // ---- compute warps ---------------------------------------------------------------------------------------------
+            for (int ly = 0; ly < nrows; ++ly) {
+                const int g = g0 + ly, st = g % RS_STAGES, pb = g % RL_PBUF;
+                mbar_wait(full + st, (unsigned)(g / RS_STAGES) & 1u);
+                const unsigned char *kblock = rl_raw + st * G::STAGE_BYTES + lane * G::PIX_BYTES + 2 * side * KS * KS;
+                float acc[RP_C];
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) acc[c] = 0.0f;
+#pragma unroll
+                for (int tk = 0; tk < G::TPW; ++tk) {
+                    const int u = u0 + tk;
+                    const unsigned char *kb = kblock + 2 * u * KS;
+                    const unsigned char *rowb = tb + 4 * ((ly + KS - 1 - u) * G::RW);
+                    if ((side + u) & 1) lane_row<KS, 1, CHB>(kb, rowb + img1, rowb + sgl1, acc);
+                    else lane_row<KS, 0, CHB>(kb, rowb + img0, rowb + sgl0, acc);
+                }
+                if (g >= RL_PBUF) mbar_wait(pempty + pb, (unsigned)(g / RL_PBUF - 1) & 1u);   // the reducer is done with this buffer
+                float *pw = part + (pb * G::NW + warp) * (RP_C * 32);
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) pw[c * 32 + lane] = acc[c];
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(empty + st); mbar_arrive(pfull + pb); }
+            }
+        }
+        g0 += nrows;
+        __syncthreads();                                    // every warp is through with this image tile
     }
 }
 
@@ -610,7 +638,10 @@ template <int KS>
 static int launch_render_lanes(const float *img, const __half *psf, int B, int H, int W, int row0, int nrw, int tone,
                                float *out_l, float *out_r, cudaStream_t st) {
     using G = LaneGeom<KS>;
-    dim3 grid(W / G::SEG, (nrw + RP_TH - 1) / RP_TH, B);
+    const int64_t n_tiles = (int64_t)(W / G::SEG) * ((nrw + RP_TH - 1) / RP_TH) * B;
+    if (n_tiles >= ((int64_t)1 << 31)) return fail(SDIRT_E_ARG, "render: too many tiles");
+    const int sms = std::max(sdirt_device_sm_count(), 1);
+    dim3 grid((unsigned)std::min<int64_t>(n_tiles, sms));
     CUDA_TRY(cudaFuncSetAttribute(render_lanes_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
     render_lanes_kernel<KS><<<grid, (G::NW + 2) * 32, G::SMEM_BYTES, st>>>(img, psf, B, H, W, row0, nrw, tone, out_l, out_r);
     return check_launch("render_lanes_kernel");

@@ -239,3 +239,35 @@ def test_every_exported_symbol_is_documented():
     names = sorted(set(re.findall(r"\b(sdirt_[a-z0-9_]+)\s*\(", hdr)))
     assert len(names) >= 30
     assert [n for n in names if n not in doc] == []
+
+
+def test_reference_arm_runs_the_unmodified_reference():
+    """bench.py's CPU legs time the UNMODIFIED reference staged under baseline/_ref (tools/stage_reference.py), not a port: every
+    staged file is byte-identical to /root/reference where that exists, the runner imports the reference's own `deeplens` (never
+    the mirror), and one tiny psf_diff call goes through."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import bench
+    import ref_runner as R
+    if not R.available():
+        pytest.skip("baseline/_ref is not staged in this checkout (python tools/stage_reference.py)")
+    if os.path.isdir("/root/reference/deeplens"):
+        import filecmp
+        for pkg in ("deeplens", "dfdp"):
+            for dp, _, fn in os.walk(os.path.join(R.REF, pkg)):
+                for f in fn:
+                    if f.endswith(".py"):
+                        staged = os.path.join(dp, f)
+                        assert filecmp.cmp(staged, os.path.join("/root/reference", os.path.relpath(staged, R.REF)), shallow=False), staged
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "deeplens" or k.startswith("deeplens.")}
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        dl = R.import_reference()
+        assert os.path.abspath(dl.__file__).startswith(R.REF)
+        rate, times, threads = bench.reference_cpu_rays_per_s(R, 1, warmup=0, sample=(4, 512))
+        assert rate > 0 and len(times) == 1 and threads >= 1
+    finally:
+        for k in [k for k in sys.modules if k == "deeplens" or k.startswith("deeplens.") or k == "dfdp" or k.startswith("dfdp.")]:
+            sys.modules.pop(k, None)
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
