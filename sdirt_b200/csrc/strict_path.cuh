@@ -219,27 +219,27 @@ __device__ __forceinline__ void strict_kill2(Ray2 &r, bool v0, bool v1) {
 }
 // The conjunction of a surface's validity tests as ONE predicate chain (setp.and) and one select per half: written out in C the
 // compiler keeps one select per test (six FSEL per pair and surface instead of two).  0f3DCCCCCD = 0.1f, 0f7FC00000 = NaN.
-// sphere, surfaces.py:464 + 667-669:  rho^2 <= r^2, t >= 0, cos^2 > 0.1, e < 1
-__device__ __forceinline__ float kill_sphere(float dz, float r2u, float r2, float t, float c2, float e) {
+// (the reference's fourth rule, no total internal reflection: e < 1, needs no test: sqrt_rn2(1 - e) is NaN for e >= 1 -- rsqrt of a
+// negative number, or 0 * inf at e = 1 -- and reaches d_z through the refraction's own arithmetic)
+// sphere, surfaces.py:464 + 667-669:  rho^2 <= r^2, t >= 0, cos^2 > 0.1
+__device__ __forceinline__ float kill_sphere(float dz, float r2u, float r2, float t, float c2) {
     float out;
     asm("{ .reg .pred p;\n\t"
         "setp.le.f32 p, %2, %3;\n\t"
         "setp.ge.and.f32 p, %4, 0f00000000, p;\n\t"
         "setp.gt.and.f32 p, %5, 0f3DCCCCCD, p;\n\t"
-        "setp.lt.and.f32 p, %6, 0f3F800000, p;\n\t"
-        "selp.f32 %0, %1, 0f7FC00000, p; }" : "=f"(out) : "f"(dz), "f"(r2u), "f"(r2), "f"(t), "f"(c2), "f"(e));
+        "selp.f32 %0, %1, 0f7FC00000, p; }" : "=f"(out) : "f"(dz), "f"(r2u), "f"(r2), "f"(t), "f"(c2));
     return out;
 }
-// asphere, surfaces.py:584 + 667-669:  rho^2 < thr, |ft| < 10e-6, t > 0, cos^2 > 0.1, e < 1
-__device__ __forceinline__ float kill_asphere(float dz, float r2u, float thr, float ft, float t, float c2, float e) {
+// asphere, surfaces.py:584 + 667-669:  rho^2 < thr, |ft| < 10e-6, t > 0, cos^2 > 0.1
+__device__ __forceinline__ float kill_asphere(float dz, float r2u, float thr, float ft, float t, float c2) {
     float out;
     asm("{ .reg .pred p;\n\t"
         "setp.lt.f32 p, %2, %3;\n\t"
         "setp.lt.and.f32 p, %4, 0f3727C5AC, p;\n\t"
         "setp.gt.and.f32 p, %5, 0f00000000, p;\n\t"
         "setp.gt.and.f32 p, %6, 0f3DCCCCCD, p;\n\t"
-        "setp.lt.and.f32 p, %7, 0f3F800000, p;\n\t"
-        "selp.f32 %0, %1, 0f7FC00000, p; }" : "=f"(out) : "f"(dz), "f"(r2u), "f"(thr), "f"(fabsf(ft)), "f"(t), "f"(c2), "f"(e));
+        "selp.f32 %0, %1, 0f7FC00000, p; }" : "=f"(out) : "f"(dz), "f"(r2u), "f"(thr), "f"(fabsf(ft)), "f"(t), "f"(c2));
     return out;
 }
 
@@ -280,7 +280,7 @@ __device__ __forceinline__ void strict_step2(const SurfDev &s, Ray2 &r, StrictWa
         const f2 nrm = sqrt_rn2(fma2(w, w, fma2(r.oy, r.oy, mul2s(r.ox, r.ox))));             // norm3
         sdiv2x3(r.ox, r.oy, w, nrm, qx, qy, qz);
         refract_strict2(s, r, qx, qy, qz, s.sigma, c2, e);
-        r.dz = make_float2(kill_sphere(r.dz.x, r2u.x, s.r2, t.x, c2.x, e.x), kill_sphere(r.dz.y, r2u.y, s.r2, t.y, c2.y, e.y));
+        r.dz = make_float2(kill_sphere(r.dz.x, r2u.x, s.r2, t.x, c2.x), kill_sphere(r.dz.y, r2u.y, s.r2, t.y, c2.y));
     } else {
         f2 g, dg;
         sag_slope_strict2<K, NAI, false, false>(s, r2u, g, dg, w);                                      // (x, y masked by ra > 0: alive here)
@@ -289,8 +289,8 @@ __device__ __forceinline__ void strict_step2(const SurfDev &s, Ray2 &r, StrictWa
         const f2 nrm = sqrt_rn2(add2(fma2(gy, gy, mul2s(gx, gx)), bc2(1.0f)));               // norm3(gx, gy, -1)
         sdiv2x3(gx, gy, bc2(-1.0f), nrm, qx, qy, qz);
         refract_strict2(s, r, qx, qy, qz, -1.0f, c2, e);
-        r.dz = make_float2(kill_asphere(r.dz.x, r2u.x, s.thr_strict, ft_last.x, t.x, c2.x, e.x),
-                           kill_asphere(r.dz.y, r2u.y, s.thr_strict, ft_last.y, t.y, c2.y, e.y));
+        r.dz = make_float2(kill_asphere(r.dz.x, r2u.x, s.thr_strict, ft_last.x, t.x, c2.x),
+                           kill_asphere(r.dz.y, r2u.y, s.thr_strict, ft_last.y, t.y, c2.y));
     }
 }
 
