@@ -17,7 +17,7 @@ try:
     print("render", d["render"]["value"], d["render"]["roofline"]["frac"], "psfnet", d["render_psfnet"]["value"], d["render_psfnet"]["roofline"]["frac"])
 except Exception as e: print("parse failed", e)
 PY
-echo "== launch list"; timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/bench_under_ncu.json 2> $OUT/bench_under_ncu.err; echo "ncu list exit $?"
+echo "== launch list"; timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/bench_under_ncu.json 2> $OUT/bench_under_ncu.err; echo "ncu list exit $?"
 python tools/launch_summary.py $OUT/bench_launches.csv > $OUT/bench_launches_summary.txt 2>&1; head -30 $OUT/bench_launches_summary.txt
 echo "== ncu full, strict bank kernel at the bench geometry"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:psf_bank_run -s 1 -c 1 -o $OUT/prof_bank_strict -f python bench.py --numerics strict --steps 1 --warmup 1 --quick > $OUT/ncu_full_strict.log 2>&1; echo "ncu full exit $?"
