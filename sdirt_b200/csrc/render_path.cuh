@@ -411,96 +411,175 @@ render_stream_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf
 // The kernels above give every pixel to a warp (lanes over taps): each lane needs its own table of tap positions,
 // the six partial sums are warp-reduced per pixel, and the 10-pairs-then-a-single rhythm of a kernel row makes most
 // shared-memory loads 2-way bank conflicted (measured: 0.44 of the HBM roofline, shared-memory pipe bound).  Here the
-// 32 lanes of a warp ARE the 32 pixels of the staged row segment and a warp owns a few whole kernel rows of one side:
+// 32 lanes of a warp ARE the 32 pixels of the staged row segment and a warp owns a few whole kernel rows of BOTH sides:
 //   * the per-pixel kernel blocks are KS*KS words apart in the stage (an odd stride): the 32 lanes of a load hit 32
 //     different banks; the image words of 32 neighbouring pixels are 16 consecutive words in each of two parity
-//     copies placed half a bank-cycle apart: conflict free as well (a third copy serves the odd-phase rows);
+//     copies placed half a bank-cycle apart: conflict free as well;
 //   * all lanes walk the same taps, so every address is lane base + immediate: no tables, no integer arithmetic;
-//   * every lane keeps its own pixel's sums: no shuffles; the 2*KS/TPW warps of a side add their partial sums
-//     through shared memory once per row.
-// Per multiply-accumulate: 1/2 LDS (kernel pair) + 3/2 LDS (image, 3 channels) + 3/2 HMUL2 + 3 FHADD per pair of taps.
+//   * kernel row u of the left and of the right kernel multiply the SAME image row, so its words are loaded once for
+//     the two (round 1 / early round 2 gave a warp rows of one side only: 8 shared-memory loads per pair of taps of
+//     the two sides, 92 % of the shared-memory pipe at the HBM roofline's pace; now 5).  The two rows start at
+//     elements of different parity in the pixel's block (KS*KS is odd), so one of them arrives shifted by one half
+//     against the image words: its kernel words are re-paired with one PRMT each (the image words are shared by three
+//     channels, the kernel words are not: permuting the kernel side costs a third of permuting the image side);
+//   * every lane keeps its own pixel's sums: no shuffles; the KS/TPW warps add their partial sums through shared
+//     memory once per row.
+// Per pair of taps of BOTH sides: 2 LDS (kernel pairs) + 3 LDS (image, 3 channels) + 1 PRMT + 6 HMUL2 + 12 FHADD.
 // ------------------------------------------------------------------------------------------------
+#ifndef SDIRT_RENDER_SPLIT_ACC
+#define SDIRT_RENDER_SPLIT_ACC 1     // the two taps of a pair sum into separate fp32 accumulators (12 independent chains per warp instead of 6)
+#endif
+#define RL_PBUF 4     // partial-sum buffers between the compute warps and the reducer warps
+#define RL_RING 32    // image rows resident (a power of two >= KS + RS_STAGES)
+
 template <int KS>
 struct LaneGeom {
     static constexpr int SEG = 32;
-    static constexpr int TPW = (KS % 3 == 0) ? 3 : 1;          // kernel rows (tasks) per warp, all of one side
-    static constexpr int NW = 2 * KS / TPW;                     // compute warps
-    static constexpr int TH = RP_TH + KS - 1, TW = SEG + KS - 1;
-    static constexpr int RW = (TW + 2) / 2;                     // words per tile row
-    static constexpr int CHW = TH * RW;                         // words per channel
-    static constexpr int COPY_RAW = RP_C * CHW;
-    // copy 1a starts at a word address == 16 (mod 32) after copy 0, copy 1b at == 17 (mod 32)
-    static constexpr int COPY1A = COPY_RAW + ((16 - COPY_RAW % 32) + 32) % 32;
-    static constexpr int COPY1B = COPY1A + COPY_RAW + ((17 - (COPY1A + COPY_RAW) % 32) + 32) % 32;
-    static constexpr int TILE_WORDS = COPY1B + COPY_RAW;
+    static constexpr int TPW = (KS % 3 == 0) ? 3 : 1;          // kernel rows (of both sides) per warp
+    static constexpr int NW = KS / TPW;                         // compute warps
+    static constexpr int NWARPS = NW + 3;                       // + one reducer per side + the streamer
+    static constexpr int TW = SEG + KS - 1;
+    static constexpr int RW = (TW + 2) / 2;                     // words per image row and channel
+    // an image-row record: what one 32-pixel strip needs of one padded image row, as the compute warps read it:
+    // copy 0 = [channel][RW words of elements (2w, 2w+1)], copy 1 = the same row shifted by one element (2w+1, 2w+2),
+    // placed at a word offset == 16 (mod 32) so that the even and the odd lanes of a load fall into different banks
+    static constexpr int COPY_RAW = RP_C * RW;
+    static constexpr int COPY1 = COPY_RAW + ((16 - COPY_RAW % 32) + 32) % 32;
+    static constexpr int REC_WORDS = (COPY1 + COPY_RAW + 3) / 4 * 4;
+    static constexpr int REC_BYTES = REC_WORDS * 4;
     static constexpr int PIX_BYTES = 2 * KS * KS * 2;
     static constexpr int STAGE_BYTES = SEG * PIX_BYTES;
-    static constexpr int TILE_OFF = RS_STAGES * STAGE_BYTES;
-    static constexpr int PART_OFF = (TILE_OFF + TILE_WORDS * 4 + 15) / 16 * 16;
-    static constexpr int PART_BYTES = 4 * NW * RP_C * 32 * 4;   // RL_PBUF buffers of [NW][C][32] floats
+    static constexpr int TILE_OFF = RS_STAGES * STAGE_BYTES;    // the ring of image-row records after the ring of kernel stages
+    static constexpr int PART_OFF = (TILE_OFF + RL_RING * REC_BYTES + 15) / 16 * 16;
+    static constexpr int PART_BYTES = RL_PBUF * NW * 2 * RP_C * 32 * 4;   // RL_PBUF buffers of [NW][side][C][32] floats
     static constexpr int BAR_OFF = PART_OFF + PART_BYTES;
-    static constexpr int SMEM_BYTES = BAR_OFF + (2 * RS_STAGES + 2 * 4) * 8;
-    static_assert(STAGE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
-    static_assert(KS % TPW == 0 && NW <= 30, "a warp's kernel rows must belong to one side; two more warps stream and reduce");
+    static constexpr int SMEM_BYTES = BAR_OFF + (2 * RS_STAGES + 2 * RL_PBUF) * 8;
+    static_assert(STAGE_BYTES % 16 == 0 && TILE_OFF % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static_assert(KS % TPW == 0 && NWARPS <= 32, "warp roles");
+    static_assert((RL_RING & (RL_RING - 1)) == 0 && RL_RING >= KS + RS_STAGES, "an image row is replaced once the output rows that read it are done");
 };
 
-// One kernel row (21 taps at KS = 21) of one side for this lane's pixel.  P0 = parity of the row's first element in the
-// pixel's block: P0 = 0 -> aligned pairs at v = 0, 2, ..., single tap v = KS-1;  P0 = 1 -> single tap v = 0, pairs at 1, 3, ...
-//   kb: this lane's kernel block + byte offset of the row's first element
-//   ib: this lane's image word address for the row's first aligned pair (copy already chosen by lane parity)
-//   sb: address of the image element (copy 0) under the row's single tap
-template <int KS, int P0, int CHB>
-__device__ __forceinline__ void lane_row(const unsigned char *kb, const unsigned char *ib, const unsigned char *sb, float (&acc)[RP_C]) {
-    constexpr int PR = (KS - 1) / 2;
+// The image as the strips read it, built once per launch: record (b, yb, tx) = padded image row row0 - pad + yb (replicate
+// padding, PSFNet.degamma applied, rounded to fp16) over the columns of strip tx, column-mirrored (so that increasing tap index
+// is increasing address), in the two pairings of LaneGeom.  ~25 B per pixel against the 1764 B of its kernels.
+// One CTA per padded image row: the row is tone-mapped, rounded, replicate-padded and MIRRORED once into shared memory
+// (element j = padded column W + KS-2 - j); strip tx's TW elements then start at j = W - 32 (tx + 1), an aligned word: copy 0 of
+// its record is a run of those words, copy 1 the same run shifted by one element (a funnel shift of two neighbouring words).
+template <int KS>
+__global__ void __launch_bounds__(256)
+render_pack_image_kernel(const float *__restrict__ img, int B, int H, int W, int row0, int nrw, int tone, unsigned *__restrict__ rec) {
+    using G = LaneGeom<KS>;
+    extern __shared__ unsigned rpk_row[];                // [RP_C][pitch] words of two fp16 each
+    constexpr int pad = (KS - 1) / 2;
+    const int tx_n = W / G::SEG, nyb = nrw + KS - 1;
+    const int wp = W + KS - 1, pitch = wp / 2 + 2;       // (W is a multiple of 32 and KS is odd: wp is even) + one word read past the end by copy 1
+    const int yb = blockIdx.x % nyb, b = blockIdx.x / nyb;
+    const int gy = min(max(row0 - pad + yb, 0), H - 1);
+#pragma unroll 5
+    for (int i = threadIdx.x; i < RP_C * pitch; i += blockDim.x) {
+        const int ch = i / pitch, jw = i - ch * pitch;
+        const float *rowp = img + (((int64_t)b * RP_C + ch) * H + gy) * W;
+        unsigned short h[2];
 #pragma unroll
-    for (int k = 0; k < PR; ++k) {
-        const __half2 kv = *reinterpret_cast<const __half2 *>(kb + 2 * P0 + 4 * k);
-#pragma unroll
-        for (int c = 0; c < RP_C; ++c) {
-            const __half2 p = __hmul2(kv, *reinterpret_cast<const __half2 *>(ib + 4 * k + c * CHB));
-            fhadd(acc[c], __low2half(p));
-            fhadd(acc[c], __high2half(p));
+        for (int k = 0; k < 2; ++k) {
+            const int j = 2 * jw + k;
+            float v = 0.0f;
+            if (j < wp) {
+                v = __ldg(rowp + min(max(wp - 1 - j - pad, 0), W - 1));
+                if (tone & 1) v = tone_degamma(v);
+            }
+            h[k] = __half_as_ushort(__float2half_rn(v));
         }
+        rpk_row[i] = (unsigned)h[0] | ((unsigned)h[1] << 16);
     }
-    const __half k1 = *reinterpret_cast<const __half *>(kb + (P0 ? 0 : 2 * (KS - 1)));
-#pragma unroll
-    for (int c = 0; c < RP_C; ++c) fhadd(acc[c], __hmul(k1, *reinterpret_cast<const __half *>(sb + c * CHB)));
+    __syncthreads();
+    unsigned *out = rec + (int64_t)blockIdx.x * tx_n * G::REC_WORDS;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < tx_n * G::REC_WORDS; i += blockDim.x) {
+        const int tx = i / G::REC_WORDS, wi = i - tx * G::REC_WORDS;
+        const int copy = wi >= G::COPY1, idx = wi - copy * G::COPY1;
+        unsigned word = 0;
+        if (idx < G::COPY_RAW) {
+            const int ch = idx / G::RW, w = idx - ch * G::RW;
+            const unsigned *src = rpk_row + ch * pitch + (W - G::SEG * (tx + 1)) / 2 + w;
+            word = copy ? __funnelshift_r(src[0], src[1], 16) : src[0];
+            const int m = 2 * w + copy;                     // elements m, m + 1 of the strip's row: nothing past its TW elements
+            if (m + 1 >= G::TW) word = m < G::TW ? (word & 0xffffu) : 0u;
+        }
+        out[i] = word;
+    }
 }
 
-#define RL_PBUF 4     // partial-sum buffers between the compute warps and the reducer warp
+// Kernel row u of both sides for this lane's pixel.  In the pixel's block one of the two rows starts at an even element
+// (aligned pairs at v = 0, 2, ..., single tap v = KS-1: `ka`) and the other at an odd one (single tap v = 0, aligned pairs at
+// v = 1, 3, ...: `kb`).  The image words are fetched once, in the pairing of the even row; the odd row's words
+// (k[2j+1], k[2j+2]) are re-paired into (k[2j], k[2j+1]) -- one PRMT each -- and its last tap is the high half of its last word.
+//   ka / kb: this lane's kernel block + byte offset of the row's first element (even / odd side)
+//   ib: this lane's image word address for the pair at v = 0 (copy already chosen by lane parity)
+//   sb: address of the image element (copy 0) under tap v = KS-1
+template <int KS, int CHB>
+__device__ __forceinline__ void lane_row_pair(const unsigned char *ka, const unsigned char *kb, const unsigned char *ib, const unsigned char *sb,
+                                              float (&acc_a)[RP_C], float (&acc_b)[RP_C], float (&hi_a)[RP_C], float (&hi_b)[RP_C]) {
+    constexpr int PR = (KS - 1) / 2;
+    unsigned prev = *reinterpret_cast<const unsigned short *>(kb);                 // k[0] of the odd row, low half
+#pragma unroll
+    for (int k = 0; k < PR; ++k) {
+        const unsigned wa = *reinterpret_cast<const unsigned *>(ka + 4 * k);
+        const unsigned wb = *reinterpret_cast<const unsigned *>(kb + 2 + 4 * k);
+        const unsigned wr = (k == 0) ? __byte_perm(prev, wb, 0x5410) : __byte_perm(prev, wb, 0x5432);
+        prev = wb;
+        const __half2 kva = *reinterpret_cast<const __half2 *>(&wa), kvb = *reinterpret_cast<const __half2 *>(&wr);
+#pragma unroll
+        for (int c = 0; c < RP_C; ++c) {
+            const __half2 im = *reinterpret_cast<const __half2 *>(ib + 4 * k + c * CHB);
+            const __half2 pa = __hmul2(kva, im), pb = __hmul2(kvb, im);
+            fhadd(acc_a[c], __low2half(pa));
+            fhadd(hi_a[c], __high2half(pa));
+            fhadd(acc_b[c], __low2half(pb));
+            fhadd(hi_b[c], __high2half(pb));
+        }
+    }
+    const __half ka1 = *reinterpret_cast<const __half *>(ka + 2 * (KS - 1));
+    const __half kb1 = __high2half(*reinterpret_cast<const __half2 *>(&prev));
+#pragma unroll
+    for (int c = 0; c < RP_C; ++c) {
+        const __half im = *reinterpret_cast<const __half *>(sb + c * CHB);
+        fhadd(acc_a[c], __hmul(ka1, im));
+        fhadd(acc_b[c], __hmul(kb1, im));
+    }
+}
 
-// Warp roles: warps 0 .. NW-1 compute (each a few kernel rows of one side, lanes = the 32 pixels of the row segment);
-// warps NW, NW+1 reduce one side each (add its NW/2 partial sums, round, tone-map, write the pixels); lane 0 of the first
-// also issues the bulk copies.  Everything between the roles is an mbarrier: compute warps never meet a CTA-wide barrier in the row loop.
-// Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the (x, y, image) grid and the ring of
-// kernel stages runs THROUGH the tile boundaries -- the streamer keeps a cursor (tile, row) of the next row to fetch and fills a
-// stage as soon as the compute warps let go of it, whether that row belongs to this tile or the next.  With one 16-row tile per
-// CTA the ring was filled and drained once per tile with nothing else resident on the SM to cover it (0.79 of the HBM roofline);
-// now the only reload between tiles is the 35 KB image tile, taken while three rows of the next tile are already in flight.
+// Warp roles: warps 0 .. NW-1 compute (each a few kernel rows of both sides, lanes = the 32 pixels of the row segment);
+// warps NW, NW+1 reduce one side each (add its NW partial sums, round, tone-map, write the pixels); lane 0 of warp NW+2 streams:
+// it issues the bulk copies.  Everything between the roles is an mbarrier: no CTA-wide barrier after the first.
+//
+// Persistent, strip-walking: the launch's 32-pixel row segments, ordered strip by strip (strip = a 32-pixel column of one image,
+// top to bottom), are cut into gridDim.x equal contiguous chunks, one per CTA (148 chunks of ~664 rows for two 1024 x 1536
+// images: balanced to one row).  Walking DOWN a strip, consecutive output rows share all but one of their KS image rows, so
+// the image lives in a ring of RL_RING row records: the bulk copy of output row i's kernels (56 KB) is followed by one of image
+// row i + KS-1 (0.8 KB, from render_pack_image_kernel's records) on the same mbarrier, into the slot of the image row that output
+// row i - (RL_RING - KS + 1) was the last to read.  No thread of the CTA touches the image on its way in -- the earlier version's
+// 16-row tiles had their 36 image rows loaded, tone-mapped and converted by the whole CTA between two tiles with every
+// compute warp waiting, about a sixth of the kernel's time (r02H profile).  Where a chunk crosses into the next strip (at most
+// twice per CTA for these images) the streamer lets the rows of the old strip finish before it sends the new strip's first
+// KS image rows (they would overwrite rows still being read): one copy latency, nothing else.
 template <int KS>
-__global__ void __launch_bounds__((LaneGeom<KS>::NW + 2) * 32, 1)
-render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ psf, int B, int H, int W, int row0, int nrw, int tone,
+__global__ void __launch_bounds__(LaneGeom<KS>::NWARPS * 32, 1)
+render_lanes_kernel(const unsigned *__restrict__ rec, const __half *__restrict__ psf, int B, int H, int W, int row0, int nrw, int tone,
                     float *__restrict__ out_l, float *__restrict__ out_r) {
     using G = LaneGeom<KS>;
     extern __shared__ __align__(128) unsigned char rl_raw[];
-    unsigned *tile = reinterpret_cast<unsigned *>(rl_raw + G::TILE_OFF);
-    __half *s0h = reinterpret_cast<__half *>(tile);
     float *part = reinterpret_cast<float *>(rl_raw + G::PART_OFF);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(rl_raw + G::BAR_OFF), *empty = full + RS_STAGES;
     unsigned long long *pfull = empty + RS_STAGES, *pempty = pfull + RL_PBUF;
-    constexpr int pad = (KS - 1) / 2, SEG = G::SEG, CHB = 4 * G::CHW;
+    constexpr int SEG = G::SEG, CHB = 4 * G::RW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tx_n = W / SEG, ty_n = (nrw + RP_TH - 1) / RP_TH;
-    const int n_tiles = tx_n * ty_n * B;
-    // tile t -> image b, first row y0, first column x0, rows in the tile
-    auto decode = [&](int t, int &b, int &y0, int &x0, int &nrows) {
-        const int tx = t % tx_n, r = t / tx_n;
-        const int ty = r % ty_n;
-        b = r / ty_n;
-        y0 = row0 + ty * RP_TH;
-        x0 = tx * SEG;
-        nrows = min(RP_TH, row0 + nrw - y0);
-    };
+    const int tx_n = W / SEG, nyb = nrw + KS - 1;
+    // this CTA's chunk of the strip-major row order: rows j0 .. j0 + n - 1; row j = row j % nrw of strip j / nrw
+    const int64_t total = (int64_t)B * tx_n * nrw;
+    const int64_t j0 = total * blockIdx.x / gridDim.x;
+    const int n = (int)(total * (blockIdx.x + 1) / gridDim.x - j0);
+    const int strip0 = (int)(j0 / nrw), yl0 = (int)(j0 - (int64_t)strip0 * nrw);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < RS_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, G::NW); }
@@ -508,92 +587,64 @@ render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ ps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // the streamer's cursor (lane 0 of the first reducer warp): next row to fetch = row p_row of tile p_t, ring position p_g
-    int p_t = blockIdx.x, p_row = 0, p_g = 0;
-    auto issue_next = [&]() {
-        int b, y0, x0, nrows;
-        decode(p_t, b, y0, x0, nrows);
-        const int st = p_g % RS_STAGES;
-        mbar_expect_tx(full + st, G::STAGE_BYTES);
-        bulk_g2s(rl_raw + st * G::STAGE_BYTES, psf + (((int64_t)b * nrw + (y0 - row0 + p_row)) * W + x0) * (2 * KS * KS), G::STAGE_BYTES, full + st);
-        ++p_g;
-        if (++p_row == nrows) { p_row = 0; p_t += gridDim.x; }
-    };
-    if (warp == G::NW && lane == 0)
-        for (int k = 0; k < RS_STAGES && p_t < n_tiles; ++k) issue_next();
 
-    // compute warps: this warp's kernel rows and this lane's pixel (constant over the tiles)
-    // pixel lx = lane; tap (u, v) multiplies mirrored tile element (row ly + KS-1-u, m = SEG-1-lane + v)
-    const int side = warp / (G::NW / 2), u0 = (warp - side * (G::NW / 2)) * G::TPW;
-    const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
-    // first aligned pair of a P0 = 0 row: v = 0, m0 = 31 - lane: odd lanes -> copy 0 word (31-lane)/2, even lanes -> copy 1a word (30-lane)/2
-    const int img0 = (lane & 1) ? 4 * ((SEG - 1 - lane) >> 1) : 4 * (G::COPY1A + ((SEG - 2 - lane) >> 1));
-    // first aligned pair of a P0 = 1 row: v = 1, m0 = 32 - lane: even lanes -> copy 0 word (32-lane)/2, odd lanes -> copy 1b word (31-lane)/2
-    const int img1 = (lane & 1) ? 4 * (G::COPY1B + ((SEG - 1 - lane) >> 1)) : 4 * ((SEG - lane) >> 1);
-    const int sgl0 = 2 * (SEG - 1 - lane + KS - 1), sgl1 = 2 * (SEG - 1 - lane);      // single taps: v = KS-1 (P0 = 0), v = 0 (P0 = 1)
-
-    int g0 = 0;                                             // rows this CTA has been through before the current tile (ring position)
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        int b, y0, x0, nrows;
-        decode(t, b, y0, x0, nrows);
-
-        // ---- image tile, column-mirrored: copy 0 (elements 2w, 2w+1 per word) and two instances of copy 1 (2w+1, 2w+2) ----
-        // loads first, eight at a time, so that a thread waits for HBM once per batch and not once per element
-        constexpr int TILE_ELEMS = RP_C * G::TH * 2 * G::RW;
-        for (int i0 = threadIdx.x; i0 < TILE_ELEMS; i0 += 8 * blockDim.x) {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = i0 + k * blockDim.x;
-                v[k] = 0.0f;
-                if (i < TILE_ELEMS) {
-                    const int c = i / (G::TH * 2 * G::RW), rem = i - c * (G::TH * 2 * G::RW);
-                    const int r = rem / (2 * G::RW), m = rem - r * (2 * G::RW);
-                    if (m < G::TW) {
-                        const int gy = min(max(y0 + r - pad, 0), H - 1), gx = min(max(x0 + (G::TW - 1 - m) - pad, 0), W - 1);
-                        v[k] = __ldg(img + (((int64_t)b * RP_C + c) * H + gy) * W + gx);
-                    }
-                }
+    if (warp == G::NW + 2) {
+        // ---- streamer ---------------------------------------------------------------------------------------------------------
+        if (lane != 0) return;
+        // next row to send: the p_g-th of the chunk = row p_yl of strip p_strip; its run (the chunk's rows in that strip) began
+        // with chunk row p_run0 at strip row p_ys
+        int p_strip = strip0, p_yl = yl0, p_g = 0, p_run0 = 0, p_ys = yl0;
+        auto issue_next = [&]() {
+            const int b = p_strip / tx_n, tx = p_strip - b * tx_n, st = p_g % RS_STAGES;
+            const int i = p_g - p_run0;                                   // row of the run
+            const int nimg = i == 0 ? KS : 1, r0 = i == 0 ? 0 : i + KS - 1;   // image rows of the run riding with it
+            mbar_expect_tx(full + st, G::STAGE_BYTES + nimg * G::REC_BYTES);
+            bulk_g2s(rl_raw + st * G::STAGE_BYTES, psf + (((int64_t)b * nrw + p_yl) * W + tx * SEG) * (2 * KS * KS), G::STAGE_BYTES, full + st);
+            for (int k = 0; k < nimg; ++k) {
+                const int r = r0 + k;                                     // image row row0 - pad + p_ys + r = record row p_ys + r
+                bulk_g2s(rl_raw + G::TILE_OFF + (r & (RL_RING - 1)) * G::REC_BYTES,
+                         rec + (((int64_t)b * nyb + p_ys + r) * tx_n + tx) * G::REC_WORDS, G::REC_BYTES, full + st);
             }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = i0 + k * blockDim.x;
-                if (i < TILE_ELEMS) {
-                    const int m = i % (2 * G::RW);
-                    s0h[i] = __float2half_rn((tone & 1) && m < G::TW ? tone_degamma(v[k]) : v[k]);
-                }
-            }
+            ++p_g;
+            if (++p_yl == nrw) { p_yl = 0; p_ys = 0; ++p_strip; p_run0 = p_g; }
+        };
+        while (p_g < n && p_g < RS_STAGES && p_run0 == 0) issue_next();
+        for (int g = 0; g < n; ++g) {
+            mbar_wait(empty + g % RS_STAGES, (unsigned)(g / RS_STAGES) & 1u);   // every compute warp has left row g (and every row before it)
+            // a stage is free once its previous row is done; a new run's image rows wait for ALL rows of the run before
+            while (p_g < n && p_g <= g + RS_STAGES && p_run0 <= g + 1) issue_next();
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < G::COPY_RAW; i += blockDim.x) {
-            const int w = i % G::RW;
-            const __half lo = s0h[2 * i + 1];
-            const __half hi = (w + 1 < G::RW) ? s0h[2 * i + 2] : __float2half_rn(0.0f);
-            const unsigned word = (unsigned)__half_as_ushort(lo) | ((unsigned)__half_as_ushort(hi) << 16);
-            tile[G::COPY1A + i] = word;
-            tile[G::COPY1B + i] = word;
-        }
-        __syncthreads();
+        return;
+    }
 
+    // compute warps: this warp's kernel rows and this lane's pixel (constant over the chunk)
+    // pixel lx = lane; tap (u, v) multiplies mirrored element m = SEG-1-lane + v of image row i + KS-1-u of the run
+    const int u0 = warp * G::TPW;
+    const unsigned char *tb = rl_raw + G::TILE_OFF;
+    // the pair at v = 0: m0 = 31 - lane: odd lanes -> copy 0 word (31-lane)/2, even lanes -> copy 1 word (30-lane)/2
+    const int img0 = (lane & 1) ? 4 * ((SEG - 1 - lane) >> 1) : 4 * (G::COPY1 + ((SEG - 2 - lane) >> 1));
+    const int sgl0 = 2 * (SEG - 1 - lane + KS - 1);                                    // the single tap v = KS-1 (copy 0, by element)
+
+    int strip = strip0, yl = yl0;
+    for (int g0 = 0; g0 < n;) {
+        // ---- a run: rows yl .. yl + rows - 1 of one strip = rows g0 .. g0 + rows - 1 of the chunk -----------------------------
+        const int rows = min(nrw - yl, n - g0);
         if (warp >= G::NW) {
-            // ---- reducer warps (one per side; the first also streams) --------------------------------------------------------
+            // ---- reducer warps (one per side) -----------------------------------------------------------------------------------
             const int s = warp - G::NW;
-            for (int ly = 0; ly < nrows; ++ly) {
-                const int g = g0 + ly, st = g % RS_STAGES, pb = g % RL_PBUF;
-                if (s == 0 && lane == 0 && p_t < n_tiles) {       // the stage of row g is free once every compute warp let go
-                    mbar_wait(empty + st, (unsigned)(g / RS_STAGES) & 1u);
-                    issue_next();                                 // row g + RS_STAGES of the ring: this tile's or the next one's
-                }
-                __syncwarp();
+            const int b = strip / tx_n, x0 = (strip - b * tx_n) * SEG;
+            float *outp = (s ? out_r : out_l) + ((int64_t)b * RP_C * H + row0 + yl) * W + x0 + lane;
+            for (int i = 0; i < rows; ++i) {
+                const int g = g0 + i, pb = g % RL_PBUF;
                 mbar_wait(pfull + pb, (unsigned)(g / RL_PBUF) & 1u);
-                const float *pr = part + pb * (G::NW * RP_C * 32);
+                const float *pr = part + pb * (G::NW * 2 * RP_C * 32);
                 float v[RP_C];
 #pragma unroll
                 for (int c = 0; c < RP_C; ++c) {
-                    const float *ps = pr + (s * (G::NW / 2)) * (RP_C * 32) + c * 32 + lane;
+                    const float *ps = pr + s * (RP_C * 32) + c * 32 + lane;
                     v[c] = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < G::NW / 2; ++k) v[c] += ps[k * (RP_C * 32)];
+                    for (int k = 0; k < G::NW; ++k) v[c] += ps[k * (2 * RP_C * 32)];
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(pempty + pb);           // the partial sums are in registers: the buffer goes back before the tone curve
@@ -601,57 +652,108 @@ render_lanes_kernel(const float *__restrict__ img, const __half *__restrict__ ps
                 for (int c = 0; c < RP_C; ++c) {
                     float o = __half2float(__float2half_rn(v[c]));
                     if (tone & 2) o = fminf(fmaxf(tone_gamma(o), 0.0f), 1.0f);
-                    (s ? out_r : out_l)[(((int64_t)b * RP_C + c) * H + (y0 + ly)) * W + (x0 + lane)] = o;
+                    outp[((int64_t)c * H + i) * W] = o;
                 }
             }
         } else {
             // ---- compute warps ---------------------------------------------------------------------------------------------
-            for (int ly = 0; ly < nrows; ++ly) {
-                const int g = g0 + ly, st = g % RS_STAGES, pb = g % RL_PBUF;
-                mbar_wait(full + st, (unsigned)(g / RS_STAGES) & 1u);
-                const unsigned char *kblock = rl_raw + st * G::STAGE_BYTES + lane * G::PIX_BYTES + 2 * side * KS * KS;
-                float acc[RP_C];
+            for (int i = 0; i < rows; ++i) {
+                const int g = g0 + i, st = g % RS_STAGES, pb = g % RL_PBUF;
+                mbar_wait(full + st, (unsigned)(g / RS_STAGES) & 1u);     // row g's kernels and image row i + KS-1 of the run (the earlier ones came before)
+                const unsigned char *kblock = rl_raw + st * G::STAGE_BYTES + lane * G::PIX_BYTES;
+                float acc[2][RP_C];
 #pragma unroll
-                for (int c = 0; c < RP_C; ++c) acc[c] = 0.0f;
+                for (int c = 0; c < RP_C; ++c) acc[0][c] = acc[1][c] = 0.0f;
+#if SDIRT_RENDER_SPLIT_ACC
+                float hi[2][RP_C];                          // the second tap of every pair sums apart: twice the independent chains
+#pragma unroll
+                for (int c = 0; c < RP_C; ++c) hi[0][c] = hi[1][c] = 0.0f;
+#else
+                float (&hi)[2][RP_C] = acc;
+#endif
 #pragma unroll
                 for (int tk = 0; tk < G::TPW; ++tk) {
                     const int u = u0 + tk;
-                    const unsigned char *kb = kblock + 2 * u * KS;
-                    const unsigned char *rowb = tb + 4 * ((ly + KS - 1 - u) * G::RW);
-                    if ((side + u) & 1) lane_row<KS, 1, CHB>(kb, rowb + img1, rowb + sgl1, acc);
-                    else lane_row<KS, 0, CHB>(kb, rowb + img0, rowb + sgl0, acc);
+                    const unsigned char *kl = kblock + 2 * u * KS, *kr = kl + 2 * KS * KS;      // row u of the left / right kernel
+                    const unsigned char *rowb = tb + ((i + KS - 1 - u) & (RL_RING - 1)) * G::REC_BYTES;
+                    // element u*KS of the block is even for even u (KS is odd): then the left row is the aligned one
+                    if (u & 1) lane_row_pair<KS, CHB>(kr, kl, rowb + img0, rowb + sgl0, acc[1], acc[0], hi[1], hi[0]);
+                    else lane_row_pair<KS, CHB>(kl, kr, rowb + img0, rowb + sgl0, acc[0], acc[1], hi[0], hi[1]);
                 }
-                if (g >= RL_PBUF) mbar_wait(pempty + pb, (unsigned)(g / RL_PBUF - 1) & 1u);   // the reducer is done with this buffer
-                float *pw = part + (pb * G::NW + warp) * (RP_C * 32);
+#if SDIRT_RENDER_SPLIT_ACC
 #pragma unroll
-                for (int c = 0; c < RP_C; ++c) pw[c * 32 + lane] = acc[c];
+                for (int c = 0; c < RP_C; ++c) { acc[0][c] += hi[0][c]; acc[1][c] += hi[1][c]; }
+#endif
+                if (g >= RL_PBUF) mbar_wait(pempty + pb, (unsigned)(g / RL_PBUF - 1) & 1u);   // the reducers are done with this buffer
+                float *pw = part + (pb * G::NW + warp) * (2 * RP_C * 32);
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int c = 0; c < RP_C; ++c) pw[(s * RP_C + c) * 32 + lane] = acc[s][c];
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(empty + st); mbar_arrive(pfull + pb); }
             }
         }
-        g0 += nrows;
-        __syncthreads();                                    // every warp is through with this image tile
+        g0 += rows;
+        yl = 0;
+        ++strip;
     }
+}
+
+// the stream-ordered pool keeps what it is given back (the default is to return it to the driver at the next synchronisation)
+static int render_pool_keep(cudaStream_t) {
+    static bool done[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+        cudaMemPool_t pool;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull;
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        done[dev] = true;
+    }
+    return 0;
 }
 
 template <int KS>
 static int launch_render_lanes(const float *img, const __half *psf, int B, int H, int W, int row0, int nrw, int tone,
                                float *out_l, float *out_r, cudaStream_t st) {
     using G = LaneGeom<KS>;
-    const int64_t n_tiles = (int64_t)(W / G::SEG) * ((nrw + RP_TH - 1) / RP_TH) * B;
-    if (n_tiles >= ((int64_t)1 << 31)) return fail(SDIRT_E_ARG, "render: too many tiles");
+    const int tx_n = W / G::SEG;
+    const int64_t total = (int64_t)B * tx_n * nrw;                                // 32-pixel row segments
+    if (total >= ((int64_t)1 << 31)) return fail(SDIRT_E_ARG, "render: too many rows");
+    if (total == 0) return 0;
+    if (int rc = render_pool_keep(st)) return rc;
+    const int64_t rec_words = (int64_t)B * (nrw + KS - 1) * tx_n * G::REC_WORDS;
+    unsigned *rec = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&rec, (size_t)rec_words * 4, st));
     const int sms = std::max(sdirt_device_sm_count(), 1);
-    dim3 grid((unsigned)std::min<int64_t>(n_tiles, sms));
-    CUDA_TRY(cudaFuncSetAttribute(render_lanes_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    render_lanes_kernel<KS><<<grid, (G::NW + 2) * 32, G::SMEM_BYTES, st>>>(img, psf, B, H, W, row0, nrw, tone, out_l, out_r);
-    return check_launch("render_lanes_kernel");
+    const size_t pack_smem = (size_t)RP_C * ((W + KS - 1) / 2 + 2) * sizeof(unsigned);
+    if (pack_smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(render_pack_image_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem);
+        if (e != cudaSuccess) { cudaFreeAsync(rec, st); return fail(SDIRT_E_CUDA, "render_pack_image_kernel: %s", cudaGetErrorString(e)); }
+    }
+    render_pack_image_kernel<KS><<<(unsigned)(B * (nrw + KS - 1)), 256, pack_smem, st>>>(img, B, H, W, row0, nrw, tone, rec);
+    int rc = check_launch("render_pack_image_kernel");
+    if (!rc) {
+        // one chunk per SM; a chunk starts by filling the image ring, so small launches take fewer, longer chunks
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(sms, total / RL_RING)));
+        cudaError_t e = cudaFuncSetAttribute(render_lanes_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+        if (e != cudaSuccess) rc = fail(SDIRT_E_CUDA, "render_lanes_kernel: %s", cudaGetErrorString(e));
+        else {
+            render_lanes_kernel<KS><<<grid, G::NWARPS * 32, G::SMEM_BYTES, st>>>(rec, psf, B, H, W, row0, nrw, tone, out_l, out_r);
+            rc = check_launch("render_lanes_kernel");
+        }
+    }
+    cudaFreeAsync(rec, st);
+    return rc;
 }
 
 // W % SEG == 0 and 16-byte aligned rows are what the bulk copies need; anything else runs the direct kernel.
 template <int KS>
 static int launch_render(const float *img, const void *psf, int psf_is_half, int B, int H, int W, int row0, int nrw, int tone,
                          float *out_l, float *out_r, cudaStream_t st) {
-    if (psf_is_half && W % 32 == 0 && ((uintptr_t)psf & 15) == 0 && LaneGeom<KS>::SMEM_BYTES <= 227 * 1024)
+    if (psf_is_half && W % 32 == 0 && W <= 32768 && ((uintptr_t)psf & 15) == 0 && LaneGeom<KS>::SMEM_BYTES <= 227 * 1024)
         return launch_render_lanes<KS>(img, (const __half *)psf, B, H, W, row0, nrw, tone, out_l, out_r, st);
     if (psf_is_half && W % 32 == 0 && ((uintptr_t)psf & 15) == 0) {
         using SG = StreamGeom<KS, __half, 32>;
