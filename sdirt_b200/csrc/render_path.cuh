@@ -469,44 +469,44 @@ template <int KS>
 __global__ void __launch_bounds__(256)
 render_pack_image_kernel(const float *__restrict__ img, int B, int H, int W, int row0, int nrw, int tone, unsigned *__restrict__ rec) {
     using G = LaneGeom<KS>;
+    static_assert(G::RW <= 32, "a warp writes one channel row of a record per pass");
     extern __shared__ unsigned rpk_row[];                // [RP_C][pitch] words of two fp16 each
     constexpr int pad = (KS - 1) / 2;
     const int tx_n = W / G::SEG, nyb = nrw + KS - 1;
     const int wp = W + KS - 1, pitch = wp / 2 + 2;       // (W is a multiple of 32 and KS is odd: wp is even) + one word read past the end by copy 1
     const int yb = blockIdx.x % nyb, b = blockIdx.x / nyb;
     const int gy = min(max(row0 - pad + yb, 0), H - 1);
-#pragma unroll 5
-    for (int i = threadIdx.x; i < RP_C * pitch; i += blockDim.x) {
-        const int ch = i / pitch, jw = i - ch * pitch;
-        const float *rowp = img + (((int64_t)b * RP_C + ch) * H + gy) * W;
-        unsigned short h[2];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int j = 2 * jw + k;
-            float v = 0.0f;
-            if (j < wp) {
-                v = __ldg(rowp + min(max(wp - 1 - j - pad, 0), W - 1));
-                if (tone & 1) v = tone_degamma(v);
-            }
-            h[k] = __half_as_ushort(__float2half_rn(v));
+    for (int ch = 0; ch < RP_C; ++ch) {
+        const float *rowp = img + (((int64_t)b * RP_C + ch) * H + gy) * W;
+#pragma unroll 4
+        for (int jw = threadIdx.x; jw < pitch; jw += blockDim.x) {
+            // elements j = 2 jw, 2 jw + 1 = image columns wp - 1 - j - pad, replicate-padded; zero past the row
+            const int x1 = wp - 1 - pad - 2 * jw;
+            float v0 = __ldg(rowp + min(max(x1, 0), W - 1)), v1 = __ldg(rowp + min(max(x1 - 1, 0), W - 1));
+            if (tone & 1) { v0 = tone_degamma(v0); v1 = tone_degamma(v1); }
+            const unsigned word = (unsigned)__half_as_ushort(__float2half_rn(v0)) | ((unsigned)__half_as_ushort(__float2half_rn(v1)) << 16);
+            rpk_row[ch * pitch + jw] = 2 * jw < wp ? word : 0u;
         }
-        rpk_row[i] = (unsigned)h[0] | ((unsigned)h[1] << 16);
     }
     __syncthreads();
-    unsigned *out = rec + (int64_t)blockIdx.x * tx_n * G::REC_WORDS;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < tx_n * G::REC_WORDS; i += blockDim.x) {
-        const int tx = i / G::REC_WORDS, wi = i - tx * G::REC_WORDS;
-        const int copy = wi >= G::COPY1, idx = wi - copy * G::COPY1;
-        unsigned word = 0;
-        if (idx < G::COPY_RAW) {
-            const int ch = idx / G::RW, w = idx - ch * G::RW;
-            const unsigned *src = rpk_row + ch * pitch + (W - G::SEG * (tx + 1)) / 2 + w;
-            word = copy ? __funnelshift_r(src[0], src[1], 16) : src[0];
-            const int m = 2 * w + copy;                     // elements m, m + 1 of the strip's row: nothing past its TW elements
-            if (m + 1 >= G::TW) word = m < G::TW ? (word & 0xffffu) : 0u;
+    // a warp per record, a lane per word of a channel row (the words between and after the two copies are never read)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int tx = warp; tx < tx_n; tx += nwarp) {
+        unsigned *out = rec + ((int64_t)blockIdx.x * tx_n + tx) * G::REC_WORDS;
+        const unsigned *src = rpk_row + (W - G::SEG * (tx + 1)) / 2 + lane;
+        if (lane < G::RW) {
+#pragma unroll
+            for (int ch = 0; ch < RP_C; ++ch) {
+                const unsigned w0 = src[ch * pitch], w1 = src[ch * pitch + 1];
+                // elements m = 2 lane (+1) of copy 0, 2 lane + 1 (+1) of copy 1: nothing past the strip's TW elements
+                unsigned c0 = w0, c1 = __funnelshift_r(w0, w1, 16);
+                if (2 * lane + 1 >= G::TW) c0 = 2 * lane < G::TW ? (c0 & 0xffffu) : 0u;
+                if (2 * lane + 2 >= G::TW) c1 = 2 * lane + 1 < G::TW ? (c1 & 0xffffu) : 0u;
+                out[ch * G::RW + lane] = c0;
+                out[G::COPY1 + ch * G::RW + lane] = c1;
+            }
         }
-        out[i] = word;
     }
 }
 
