@@ -220,6 +220,19 @@ int sdirt_render_local_psf_rows(const float *img_dev, const void *psf_rows_dev, 
                                 int B, int C, int H, int W, int row0, int n_rows, int ks, int tone,
                                 float *out_l_dev, float *out_r_dev, void *stream);
 
+/* The banded render with the image prepared ONCE per PSFNet.render call instead of once per band (psfnet.py:706-708: the
+ * reference's degamma / local_psf_render_fast see the whole image once).  The strip-walking render kernel reads the image as
+ * "records" (replicate-padded rows, degamma applied, rounded to fp16, column-mirrored per 32-pixel strip):
+ *   sdirt_render_records_bytes: size of that buffer for a [B,C,H,W] image, or 0 when the kernel does not take the shape
+ *     (it takes C = 3, W a multiple of 32, ks 7 / 11 / 21: other callers use sdirt_render_local_psf_rows);
+ *   sdirt_render_pack_image: img[B,C,H,W] float32 -> records (tone bit 1 = degamma first);
+ *   sdirt_render_local_psf_rows_packed: sdirt_render_local_psf_rows from those records and float16 kernels
+ *     psf_rows_half_dev[B, n_rows, W, 2, ks, ks] (tone bit 2 = gamma + clip on the output).  Both buffers 16-byte aligned. */
+int64_t sdirt_render_records_bytes(int B, int C, int H, int W, int ks);
+int sdirt_render_pack_image(const float *img_dev, int B, int C, int H, int W, int ks, int tone, void *records_dev, void *stream);
+int sdirt_render_local_psf_rows_packed(const void *records_dev, const void *psf_rows_half_dev, int B, int C, int H, int W,
+                                       int row0, int n_rows, int ks, int tone, float *out_l_dev, float *out_r_dev, void *stream);
+
 /* ---- the two ends of PSFNet.pred inside PSFNet.render (psfnet.py:317-336, 681-705; psfnet_arch.py:40-41) ----------
  * sdirt_mlp_input_layer: for the pixels of images [b0, b0 + nb), rows [row0, row0 + n_rows) build the MLP's first
  * activation.  Pixel p = ((b - b0) * n_rows + (y - row0)) * W + x owns output rows 2p (left: input (xs[x], ys[y],

@@ -77,6 +77,11 @@ def lib():
     L.sdirt_render_local_psf.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
     L.sdirt_render_local_psf_rows.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
     L.sdirt_render_local_psf_f32.argtypes = [vp, vp, cint, cint, cint, cint, cint, vp, vp, vp]
+    if hasattr(L, "sdirt_render_records_bytes") or not os.environ.get("SDIRT_ENGINE_LIB"):     # (an older build loaded for an A/B run may lack them)
+        L.sdirt_render_records_bytes.argtypes = [cint, cint, cint, cint, cint]
+        L.sdirt_render_records_bytes.restype = i64
+        L.sdirt_render_pack_image.argtypes = [vp, cint, cint, cint, cint, cint, cint, vp, vp]
+        L.sdirt_render_local_psf_rows_packed.argtypes = [vp, vp, cint, cint, cint, cint, cint, cint, cint, cint, vp, vp, vp]
     L.sdirt_mlp_input_layer.argtypes = [vp, vp, vp, cint, cint, cint, cint, cint, cint, cint, vp, vp, cint, vp, vp]
     L.sdirt_psf_pack.argtypes = [vp, i64, cint, cint, vp, vp]
     L.sdirt_mlp_fused_layout.argtypes = [C.POINTER(MlpShape), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(i64)]
@@ -394,6 +399,34 @@ def render_local_psf_rows(img, psf_rows, ks, row0, out_l, out_r, tone=0):
     _check(lib().sdirt_render_local_psf_rows(_dev(img, "img"), _dev(psf_rows, "psf_rows", psf_rows.dtype),
                                              int(psf_rows.dtype == torch.float16), b, c, h, w, int(row0), int(n_rows), int(ks),
                                              int(tone), _dev(out_l, "out_l"), _dev(out_r, "out_r"), _stream(img)))
+    return out_l, out_r
+
+
+@_on_device
+def render_pack_image(img, ks, tone=0):
+    """The image as the strip-walking render kernel streams it (records: padded, degamma'd if tone & 1, fp16), packed once for all
+    the bands of a PSFNet.render call; None when that kernel does not take the shape (the caller then uses render_local_psf_rows)."""
+    b, c, h, w = img.shape
+    n = lib().sdirt_render_records_bytes(b, c, h, w, int(ks))
+    if n <= 0:
+        return None
+    rec = torch.empty((n,), device=img.device, dtype=torch.uint8)
+    _check(lib().sdirt_render_pack_image(_dev(img, "img"), b, c, h, w, int(ks), int(tone), _dev(rec, "records", torch.uint8), _stream(img)))
+    return rec
+
+
+@_on_device
+def render_local_psf_rows_packed(rec, shape, psf_rows, ks, row0, out_l, out_r, tone=0):
+    """render_local_psf_rows from the records of render_pack_image (`shape` = the image's [B,C,H,W]); psf_rows float16."""
+    b, c, h, w = shape
+    n_rows = psf_rows.shape[1]
+    if psf_rows.dtype != torch.float16 or psf_rows.dim() != 6 or psf_rows.numel() != b * n_rows * w * 2 * ks * ks:
+        raise RuntimeError("sdirt_engine: psf_rows must be float16 [B,n_rows,W,2,ks,ks]")
+    if tuple(out_l.shape) != tuple(shape) or tuple(out_r.shape) != tuple(shape):
+        raise RuntimeError("sdirt_engine: outputs must have the image's shape")
+    _check(lib().sdirt_render_local_psf_rows_packed(_dev(rec, "records", torch.uint8), _dev(psf_rows, "psf_rows", torch.float16), b, c, h, w,
+                                                    int(row0), int(n_rows), int(ks), int(tone), _dev(out_l, "out_l"), _dev(out_r, "out_r"),
+                                                    _stream(out_l)))
     return out_l, out_r
 
 

@@ -565,8 +565,8 @@ __device__ __forceinline__ void lane_row_pair(const unsigned char *ka, const uns
 // KS image rows (they would overwrite rows still being read): one copy latency, nothing else.
 template <int KS>
 __global__ void __launch_bounds__(LaneGeom<KS>::NWARPS * 32, 1)
-render_lanes_kernel(const unsigned *__restrict__ rec, const __half *__restrict__ psf, int B, int H, int W, int row0, int nrw, int tone,
-                    float *__restrict__ out_l, float *__restrict__ out_r) {
+render_lanes_kernel(const unsigned *__restrict__ rec, int rec_nyb, int rec_y0, const __half *__restrict__ psf, int B, int H, int W, int row0, int nrw,
+                    int tone, float *__restrict__ out_l, float *__restrict__ out_r) {
     using G = LaneGeom<KS>;
     extern __shared__ __align__(128) unsigned char rl_raw[];
     float *part = reinterpret_cast<float *>(rl_raw + G::PART_OFF);
@@ -574,7 +574,8 @@ render_lanes_kernel(const unsigned *__restrict__ rec, const __half *__restrict__
     unsigned long long *pfull = empty + RS_STAGES, *pempty = pfull + RL_PBUF;
     constexpr int SEG = G::SEG, CHB = 4 * G::RW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tx_n = W / SEG, nyb = nrw + KS - 1;
+    const int tx_n = W / SEG;
+    // (rec holds rec_nyb record rows per image; record row rec_y0 is padded image row row0 - pad)
     // this CTA's chunk of the strip-major row order: rows j0 .. j0 + n - 1; row j = row j % nrw of strip j / nrw
     const int64_t total = (int64_t)B * tx_n * nrw;
     const int64_t j0 = total * blockIdx.x / gridDim.x;
@@ -601,9 +602,9 @@ render_lanes_kernel(const unsigned *__restrict__ rec, const __half *__restrict__
             mbar_expect_tx(full + st, G::STAGE_BYTES + nimg * G::REC_BYTES);
             bulk_g2s(rl_raw + st * G::STAGE_BYTES, psf + (((int64_t)b * nrw + p_yl) * W + tx * SEG) * (2 * KS * KS), G::STAGE_BYTES, full + st);
             for (int k = 0; k < nimg; ++k) {
-                const int r = r0 + k;                                     // image row row0 - pad + p_ys + r = record row p_ys + r
+                const int r = r0 + k;                                     // image row row0 - pad + p_ys + r = record row rec_y0 + p_ys + r
                 bulk_g2s(rl_raw + G::TILE_OFF + (r & (RL_RING - 1)) * G::REC_BYTES,
-                         rec + (((int64_t)b * nyb + p_ys + r) * tx_n + tx) * G::REC_WORDS, G::REC_BYTES, full + st);
+                         rec + (((int64_t)b * rec_nyb + rec_y0 + p_ys + r) * tx_n + tx) * G::REC_WORDS, G::REC_BYTES, full + st);
             }
             ++p_g;
             if (++p_yl == nrw) { p_yl = 0; p_ys = 0; ++p_strip; p_run0 = p_g; }
@@ -715,36 +716,47 @@ static int render_pool_keep(cudaStream_t) {
     return 0;
 }
 
+// can the strip-walking kernel take this shape?  (fp16 kernels, 16-byte aligned, are the caller's to check)
+template <int KS>
+static bool render_lanes_ok(int W) { return W % 32 == 0 && W <= 32768 && LaneGeom<KS>::SMEM_BYTES <= 227 * 1024; }
+template <int KS>
+static int64_t render_records_bytes(int B, int n_rows, int W) {
+    return (int64_t)B * (n_rows + KS - 1) * (W / LaneGeom<KS>::SEG) * LaneGeom<KS>::REC_BYTES;
+}
+
+// records of padded image rows row0 - pad .. row0 + nrw - 1 + pad of every image
+template <int KS>
+static int launch_render_pack(const float *img, int B, int H, int W, int row0, int nrw, int tone, unsigned *rec, cudaStream_t st) {
+    const size_t pack_smem = (size_t)RP_C * ((W + KS - 1) / 2 + 2) * sizeof(unsigned);
+    if (pack_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(render_pack_image_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem));
+    render_pack_image_kernel<KS><<<(unsigned)(B * (nrw + KS - 1)), 256, pack_smem, st>>>(img, B, H, W, row0, nrw, tone, rec);
+    return check_launch("render_pack_image_kernel");
+}
+
+// rows [row0, row0 + nrw) from records: rec holds rec_nyb record rows per image, record row rec_y0 = padded image row row0 - pad
+template <int KS>
+static int launch_render_strips(const unsigned *rec, int rec_nyb, int rec_y0, const __half *psf, int B, int H, int W, int row0, int nrw, int tone,
+                                float *out_l, float *out_r, cudaStream_t st) {
+    using G = LaneGeom<KS>;
+    const int64_t total = (int64_t)B * (W / G::SEG) * nrw;                       // 32-pixel row segments
+    if (total >= ((int64_t)1 << 31)) return fail(SDIRT_E_ARG, "render: too many rows");
+    if (total == 0) return 0;
+    const int sms = std::max(sdirt_device_sm_count(), 1);
+    // one chunk per SM (a chunk starts by fetching KS image rows: not fewer than 8 output rows per chunk)
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(sms, total / 8)));
+    CUDA_TRY(cudaFuncSetAttribute(render_lanes_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+    render_lanes_kernel<KS><<<grid, G::NWARPS * 32, G::SMEM_BYTES, st>>>(rec, rec_nyb, rec_y0, psf, B, H, W, row0, nrw, tone, out_l, out_r);
+    return check_launch("render_lanes_kernel");
+}
+
 template <int KS>
 static int launch_render_lanes(const float *img, const __half *psf, int B, int H, int W, int row0, int nrw, int tone,
                                float *out_l, float *out_r, cudaStream_t st) {
-    using G = LaneGeom<KS>;
-    const int tx_n = W / G::SEG;
-    const int64_t total = (int64_t)B * tx_n * nrw;                                // 32-pixel row segments
-    if (total >= ((int64_t)1 << 31)) return fail(SDIRT_E_ARG, "render: too many rows");
-    if (total == 0) return 0;
     if (int rc = render_pool_keep(st)) return rc;
-    const int64_t rec_words = (int64_t)B * (nrw + KS - 1) * tx_n * G::REC_WORDS;
     unsigned *rec = nullptr;
-    CUDA_TRY(cudaMallocAsync((void **)&rec, (size_t)rec_words * 4, st));
-    const int sms = std::max(sdirt_device_sm_count(), 1);
-    const size_t pack_smem = (size_t)RP_C * ((W + KS - 1) / 2 + 2) * sizeof(unsigned);
-    if (pack_smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(render_pack_image_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem);
-        if (e != cudaSuccess) { cudaFreeAsync(rec, st); return fail(SDIRT_E_CUDA, "render_pack_image_kernel: %s", cudaGetErrorString(e)); }
-    }
-    render_pack_image_kernel<KS><<<(unsigned)(B * (nrw + KS - 1)), 256, pack_smem, st>>>(img, B, H, W, row0, nrw, tone, rec);
-    int rc = check_launch("render_pack_image_kernel");
-    if (!rc) {
-        // one chunk per SM; a chunk starts by filling the image ring, so small launches take fewer, longer chunks
-        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(sms, total / RL_RING)));
-        cudaError_t e = cudaFuncSetAttribute(render_lanes_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
-        if (e != cudaSuccess) rc = fail(SDIRT_E_CUDA, "render_lanes_kernel: %s", cudaGetErrorString(e));
-        else {
-            render_lanes_kernel<KS><<<grid, G::NWARPS * 32, G::SMEM_BYTES, st>>>(rec, psf, B, H, W, row0, nrw, tone, out_l, out_r);
-            rc = check_launch("render_lanes_kernel");
-        }
-    }
+    CUDA_TRY(cudaMallocAsync((void **)&rec, (size_t)render_records_bytes<KS>(B, nrw, W), st));
+    int rc = launch_render_pack<KS>(img, B, H, W, row0, nrw, tone, rec, st);
+    if (!rc) rc = launch_render_strips<KS>(rec, nrw + KS - 1, 0, psf, B, H, W, row0, nrw, tone, out_l, out_r, st);
     cudaFreeAsync(rec, st);
     return rc;
 }
@@ -753,7 +765,7 @@ static int launch_render_lanes(const float *img, const __half *psf, int B, int H
 template <int KS>
 static int launch_render(const float *img, const void *psf, int psf_is_half, int B, int H, int W, int row0, int nrw, int tone,
                          float *out_l, float *out_r, cudaStream_t st) {
-    if (psf_is_half && W % 32 == 0 && W <= 32768 && ((uintptr_t)psf & 15) == 0 && LaneGeom<KS>::SMEM_BYTES <= 227 * 1024)
+    if (psf_is_half && ((uintptr_t)psf & 15) == 0 && render_lanes_ok<KS>(W))
         return launch_render_lanes<KS>(img, (const __half *)psf, B, H, W, row0, nrw, tone, out_l, out_r, st);
     if (psf_is_half && W % 32 == 0 && ((uintptr_t)psf & 15) == 0) {
         using SG = StreamGeom<KS, __half, 32>;

@@ -316,7 +316,12 @@ class PSFNet(Lensgroup):
         ys = torch.linspace(1, -1, H).to(img.device)
         (w1, b1), chain = self._mlp_half_layers()
         img32 = img.float().contiguous()
-        if tone & 1:                                                       # degamma once per call, not per band and tile halo
+        # the image as the strip-walking render kernel streams it (padded, degamma'd, fp16), once per call and not per band;
+        # None for shapes that kernel does not take (other channel counts / widths / kernel sizes): then degamma once per call
+        rec = E.render_pack_image(img32, ks, tone & 1)
+        if rec is not None:
+            tone &= ~1
+        elif tone & 1:
             img32, tone = E.tone_degamma(img32, out=img32 if img32.data_ptr() != img.data_ptr() else None), tone & ~1
         rl, rr = torch.empty_like(img32), torch.empty_like(img32)
         use_fused = self.mlp_engine == "fused" and self._mlp_fused() is not None
@@ -364,8 +369,13 @@ class PSFNet(Lensgroup):
                     post.wait_event(ready[k])
                     if not packed:
                         E.psf_pack(raw[k][:2 * px], ks, out=psf[k][:px])
-                    E.render_local_psf_rows(img32[b0:b0 + nbb], psf[k][:px].view(nbb, nr, W, 2, ks, ks), ks, y0,
-                                            rl[b0:b0 + nbb], rr[b0:b0 + nbb], tone=tone)
+                    if rec is not None:
+                        nrec = rec.numel() // N
+                        E.render_local_psf_rows_packed(rec[b0 * nrec:(b0 + nbb) * nrec], (nbb, C, H, W), psf[k][:px].view(nbb, nr, W, 2, ks, ks),
+                                                       ks, y0, rl[b0:b0 + nbb], rr[b0:b0 + nbb], tone=tone)
+                    else:
+                        E.render_local_psf_rows(img32[b0:b0 + nbb], psf[k][:px].view(nbb, nr, W, 2, ks, ks), ks, y0,
+                                                rl[b0:b0 + nbb], rr[b0:b0 + nbb], tone=tone)
                     if post is not main:
                         buf_free[k] = torch.cuda.Event()
                         buf_free[k].record(post)

@@ -629,6 +629,37 @@ def test_render_rows_equals_whole_image():
         E.render_local_psf_rows(img, psf[:, :4].contiguous(), ks, H - 2, bl, br)
 
 
+def test_render_rows_from_packed_image():
+    """The image packed once (sdirt_render_pack_image) and convolved band by band from the records is bit-identical to the whole-image
+    call, whatever the cuts (chunks that start inside a strip, cross into the next strip or image, single-row bands), for every
+    kernel size the packed render takes; shapes it does not take are refused by the size query."""
+    from sdirt_b200 import _engine as E
+    gen = torch.Generator(device=DEV).manual_seed(14)
+    for (B, H, W, ks, cuts) in ((2, 40, 64, 21, (0, 16, 21, 40)), (1, 75, 96, 21, (0, 1, 2, 33, 74, 75)), (3, 23, 32, 7, (0, 23)),
+                                (2, 50, 64, 11, (0, 7, 50))):
+        img = torch.rand((B, 3, H, W), device=DEV, generator=gen)
+        psf = torch.rand((B, H, W, 2, ks, ks), device=DEV, generator=gen) ** 3
+        psf = (psf / psf.sum((-1, -2), keepdim=True)).half().contiguous()
+        for tone in (0, 3):
+            rl, rr = E.render_local_psf(img, psf, ks, tone=tone)
+            rec = E.render_pack_image(img, ks, tone & 1)
+            assert rec is not None
+            bl, br = torch.full_like(img, -1.0), torch.full_like(img, -1.0)
+            for y0, y1 in zip(cuts[:-1], cuts[1:]):
+                E.render_local_psf_rows_packed(rec, img.shape, psf[:, y0:y1].contiguous(), ks, y0, bl, br, tone=tone)
+            assert torch.equal(bl, rl) and torch.equal(br, rr)
+        # one image of the batch from its slice of the records
+        nrec = rec.numel() // B
+        bl, br = torch.full_like(img[:1], -1.0), torch.full_like(img[:1], -1.0)
+        E.render_local_psf_rows_packed(rec[(B - 1) * nrec:], (1, 3, H, W), psf[B - 1:], ks, 0, bl, br, tone=3)
+        assert torch.equal(bl, rl[B - 1:]) and torch.equal(br, rr[B - 1:])
+    assert E.render_pack_image(torch.rand((1, 3, 8, 40), device=DEV), 21) is None          # W not a multiple of 32
+    assert E.render_pack_image(torch.rand((1, 3, 8, 64), device=DEV), 9) is None           # kernel size without the strip kernel
+    assert E.render_pack_image(torch.rand((1, 2, 8, 64), device=DEV), 21) is None          # not RGB
+    with pytest.raises(RuntimeError):
+        E.render_local_psf_rows_packed(rec, img.shape, psf[:, :4].contiguous(), ks, H - 2, torch.empty_like(img), torch.empty_like(img))
+
+
 def test_gamma_noise_clip_vs_oracle():
     from sdirt_b200 import _engine as E
     rng = np.random.default_rng(8)
