@@ -492,7 +492,7 @@ def run_gpu(args):
         low = torch.rand((nloc, 1, rh // 64 + 2, rw // 64 + 2), device=dev, generator=g)
         depth = -(torch.nn.functional.interpolate(low, size=(rh, rw), mode="bilinear", align_corners=False) * 9750 + 250)
         foc = torch.full((nloc,), -1000.0, device=dev)
-        rlens.render(img[:1], depth[:1], foc[:1])
+        rlens.render(img, depth, foc)                                  # warm-up at the timed shape (band buffers, image records)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -241,7 +241,9 @@ class PSFNet(Lensgroup):
     def _fused_band_shape(self, N, H, W):
         """(rows, images) of a band for the fused engine.  Its persistent kernel gives every CTA pair groups of 128 pixels, so a
         band costs ceil(pixels / 128 / (SMs / 2)) rounds: pick the shape under the pixel budget that wastes the least of its
-        last round (98304 pixels = 10.4 rounds cost 11; 196608 = 20.8 cost 21).  Rows in multiples of the render kernels' 16."""
+        last round (98304 pixels = 10.4 rounds cost 11; 196608 = 20.8 cost 21) -- weighed against what a short band costs the
+        render kernel, which walks 32-pixel strips downwards and pays ~3 rows' time (KS image rows to fetch, one copy latency)
+        wherever a strip of the band ends.  The convolution is ~5 % of a band's time."""
         if "render_band_rows" in self.__dict__ or "render_band_pixels" in self.__dict__:      # set by hand: keep
             rows = max(1, min(int(self.render_band_rows), H))
             return rows, max(1, min(N, int(self.render_band_pixels) // (rows * W)))
@@ -254,7 +256,8 @@ class PSFNet(Lensgroup):
                 if px > max(int(self.render_band_pixels_fused), rows * W) and nb > 1:
                     break
                 rounds = -(-px // 128) / slots
-                score = (round(rounds / -(-rounds // 1), 3), px)
+                mlp_eff, conv_eff = rounds / -(-rounds // 1), rows / (rows + 3.0)
+                score = (round(1.0 / (0.95 / mlp_eff + 0.05 / conv_eff), 3), px)
                 if best is None or score > best[0]:
                     best = (score, rows, nb)
         return best[1], best[2]
