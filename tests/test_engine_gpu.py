@@ -636,7 +636,7 @@ def test_render_rows_from_packed_image():
     from sdirt_b200 import _engine as E
     gen = torch.Generator(device=DEV).manual_seed(14)
     for (B, H, W, ks, cuts) in ((2, 40, 64, 21, (0, 16, 21, 40)), (1, 75, 96, 21, (0, 1, 2, 33, 74, 75)), (3, 23, 32, 7, (0, 23)),
-                                (2, 50, 64, 11, (0, 7, 50))):
+                                (2, 50, 64, 11, (0, 7, 50)), (1, 5, 32, 21, (0, 2, 5)), (5, 3, 32, 11, (0, 3)), (1, 300, 160, 21, (0, 300))):
         img = torch.rand((B, 3, H, W), device=DEV, generator=gen)
         psf = torch.rand((B, H, W, 2, ks, ks), device=DEV, generator=gen) ** 3
         psf = (psf / psf.sum((-1, -2), keepdim=True)).half().contiguous()
