@@ -429,6 +429,9 @@ render_stream_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf
 #ifndef SDIRT_RENDER_SPLIT_ACC
 #define SDIRT_RENDER_SPLIT_ACC 1     // the two taps of a pair sum into separate fp32 accumulators (12 independent chains per warp instead of 6)
 #endif
+#ifndef SDIRT_RENDER_REDUCERS_SAME_SMSP
+#define SDIRT_RENDER_REDUCERS_SAME_SMSP 1
+#endif
 #define RL_PBUF 4     // partial-sum buffers between the compute warps and the reducer warps
 #define RL_RING 32    // image rows resident (a power of two >= KS + RS_STAGES)
 
@@ -437,7 +440,19 @@ struct LaneGeom {
     static constexpr int SEG = 32;
     static constexpr int TPW = (KS % 3 == 0) ? 3 : 1;          // kernel rows (of both sides) per warp
     static constexpr int NW = KS / TPW;                         // compute warps
+#if SDIRT_RENDER_REDUCERS_SAME_SMSP
+    // + one reducer per side + the streamer.  Warp w issues from scheduler w % 4: with 7 (11) compute warps scheduler 3 has one
+    // compute warp fewer than the others, so BOTH reducers go there (warp ids = 3 mod 4: their ~200 instructions per row -- sums,
+    // rounding, tone curve, stores -- would otherwise delay the two compute warps of scheduler 0, and the slowest compute warp
+    // paces the CTA); the warps in between have no role and leave at once.
+    static constexpr int RED0 = NW + ((3 - NW % 4) + 4) % 4;     // the first warp id past the compute warps that is 3 mod 4
+    static constexpr int RED1 = RED0 + 4, STREAM = RED0 + 1;
+    static constexpr int NWARPS = RED1 + 1;
+#else
+    static constexpr int RED0 = NW, RED1 = NW + 1, STREAM = NW + 2;
     static constexpr int NWARPS = NW + 3;                       // + one reducer per side + the streamer
+#endif
+    static_assert(RED0 >= NW && STREAM > RED0 && STREAM != RED1, "warp roles");
     static constexpr int TW = SEG + KS - 1;
     static constexpr int RW = (TW + 2) / 2;                     // words per image row and channel
     // an image-row record: what one 32-pixel strip needs of one padded image row, as the compute warps read it:
@@ -589,7 +604,8 @@ render_lanes_kernel(const unsigned *__restrict__ rec, int rec_nyb, int rec_y0, c
     }
     __syncthreads();
 
-    if (warp == G::NW + 2) {
+    if (warp >= G::NW && warp != G::RED0 && warp != G::RED1 && warp != G::STREAM) return;       // no role
+    if (warp == G::STREAM) {
         // ---- streamer ---------------------------------------------------------------------------------------------------------
         if (lane != 0) return;
         // next row to send: the p_g-th of the chunk = row p_yl of strip p_strip; its run (the chunk's rows in that strip) began
@@ -632,7 +648,7 @@ render_lanes_kernel(const unsigned *__restrict__ rec, int rec_nyb, int rec_y0, c
         const int rows = min(nrw - yl, n - g0);
         if (warp >= G::NW) {
             // ---- reducer warps (one per side) -----------------------------------------------------------------------------------
-            const int s = warp - G::NW;
+            const int s = warp == G::RED1;
             const int b = strip / tx_n, x0 = (strip - b * tx_n) * SEG;
             float *outp = (s ? out_r : out_l) + ((int64_t)b * RP_C * H + row0 + yl) * W + x0 + lane;
             for (int i = 0; i < rows; ++i) {
