@@ -58,6 +58,9 @@ __device__ __forceinline__ void poly_terms2(const SurfDev &s, f2 r2, f2 &g, f2 &
 #ifndef SDIRT_STRICT_SHORT_DIV
 #define SDIRT_STRICT_SHORT_DIV 1
 #endif
+#ifndef SDIRT_STRICT_CYCLE_FROM
+#define SDIRT_STRICT_CYCLE_FROM 3     // first evaluation of the first surface's Newton loop that looks for a fixed point / 2-cycle of t (>= 2)
+#endif
 #ifndef SDIRT_STRICT_RCP_SQUARE
 #define SDIRT_STRICT_RCP_SQUARE 0     // experiment: relieve the XU pipe (one MUFU.RCP less per evaluation) at one more packed multiply
 #endif
@@ -171,7 +174,7 @@ __device__ __forceinline__ void newton_strict2(const SurfDev &s, const Ray2 &r, 
         f2 ftn, tn;
         newton_eval2<KIND, NAI, false>(s, r, a, b, t, ftn, tn, w);
         ++it;
-        if (FIRST && it >= 3) {
+        if (FIRST && it >= SDIRT_STRICT_CYCLE_FROM) {
             // period 1 (t_new == t): every further evaluation repeats this one.  period 2 (t_new == the t before this
             // evaluation's input) with the residual still above the tolerance: t alternates until the cap, the parity of
             // the evaluations left picks the survivor.  Looked for from the third evaluation on (a ray that converges the
