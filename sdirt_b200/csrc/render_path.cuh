@@ -418,7 +418,8 @@ render_stream_kernel(const float *__restrict__ img, const PsfT *__restrict__ psf
 //   * all lanes walk the same taps, so every address is lane base + immediate: no tables, no integer arithmetic;
 //   * kernel row u of the left and of the right kernel multiply the SAME image row, so its words are loaded once for
 //     the two (round 1 / early round 2 gave a warp rows of one side only: 8 shared-memory loads per pair of taps of
-//     the two sides, 92 % of the shared-memory pipe at the HBM roofline's pace; now 5).  The two rows start at
+//     the two sides; now 5, and 12 % fewer instructions per row in all -- the issue slots, not the shared-memory pipe,
+//     were what the earlier kernel ran out of at the HBM roofline's pace).  The two rows start at
 //     elements of different parity in the pixel's block (KS*KS is odd), so one of them arrives shifted by one half
 //     against the image words: its kernel words are re-paired with one PRMT each (the image words are shared by three
 //     channels, the kernel words are not: permuting the kernel side costs a third of permuting the image side);
