@@ -230,6 +230,22 @@ def test_fused_mlp_layout_host_side():
         assert lib.sdirt_last_error()
 
 
+def test_render_records_size_host_side():
+    """sdirt_render_records_bytes is host arithmetic: one record per padded image row and 32-pixel strip -- 3 channels x 27 words in
+    two pairings, the second at a word offset of 16 (mod 32), rounded to 16 bytes (784 B at ks = 21, 592 B at 11, 560 B at 7) --,
+    0 for the shapes the strip-walking render kernel does not take; the packed entries refuse those shapes without a device."""
+    from sdirt_b200 import _engine as E
+    lib = E.lib()
+    assert lib.sdirt_render_records_bytes(2, 3, 1024, 1536, 21) == 2 * (1024 + 20) * 48 * 784 == 78575616
+    assert lib.sdirt_render_records_bytes(1, 3, 512, 768, 11) == (512 + 10) * 24 * 592
+    assert lib.sdirt_render_records_bytes(4, 3, 64, 32, 7) == 4 * (64 + 6) * 1 * 560
+    for b, c, h, w, ks in ((1, 3, 64, 40, 21), (1, 3, 64, 64, 9), (1, 1, 64, 64, 21), (1, 4, 64, 64, 21), (0, 3, 64, 64, 21), (1, 3, 64, 65536, 21)):
+        assert lib.sdirt_render_records_bytes(b, c, h, w, ks) == 0
+    assert lib.sdirt_render_pack_image(None, 1, 3, 64, 40, 21, 0, None, None) < 0 and b"packed render" in lib.sdirt_last_error()
+    assert lib.sdirt_render_local_psf_rows_packed(None, None, 1, 3, 64, 64, 60, 8, 21, 0, None, None, None) < 0 and b"outside the image" in lib.sdirt_last_error()
+    assert lib.sdirt_render_local_psf_rows_packed(None, None, 1, 3, 64, 64, 0, 8, 21, 0, None, None, None) < 0 and b"null buffer" in lib.sdirt_last_error()
+
+
 def test_every_exported_symbol_is_documented():
     """The drop-in boundary is the header: every entry point it declares appears, by its full name, in INTEGRATION.md's table of
     what it replaces in the reference."""
