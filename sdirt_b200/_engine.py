@@ -358,7 +358,9 @@ def render_local_psf(img, psf, ks, tone=0):
     """img [B,C,H,W] float32, psf [B,H,W,2,ks,ks] float32/float16 -> (rl, rr) float32.
     tone bits: 1 = degamma the input, 2 = gamma + clip the output."""
     b, c, h, w = img.shape
-    if tone & 1:                       # once per pixel here instead of once per tile halo inside the kernel (same bits)
+    # degamma once per pixel instead of once per tile halo inside the kernel (same bits) -- unless the call takes the strip-walking
+    # kernel, whose image-record pack applies it once per pixel itself
+    if tone & 1 and not (psf.dtype == torch.float16 and lib().sdirt_render_records_bytes(b, c, h, w, int(ks)) > 0):
         img, tone = tone_degamma(img), tone & ~1
     if psf.dtype not in (torch.float32, torch.float16):
         raise RuntimeError("sdirt_engine: psf must be float32 or float16")
